@@ -1,0 +1,785 @@
+// C-ABI implementation (include/nmma_b200.h): handle, one-time staging of the
+// surrogate / observation tables into device buffers, and kernel dispatch.
+#include "../../include/nmma_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace nmma;
+
+namespace {
+thread_local std::string g_create_error;
+constexpr int kVersion = 100;  // 0.1.0
+constexpr long long kTwoStageChunk = 1 << 18;  // points per coefficient-scratch chunk
+}  // namespace
+
+struct nmma_b200_handle {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    // ---- host copies of the configuration ----
+    int F = 0, d = 0, K = 0, T = 0;
+    std::vector<double> tt, pmin, pmax, VA, mins, maxs;
+    bool have_svd = false;
+    int kind = -1;  // 0 mlp, 1 gp
+    int H = 0, Kout = 0;
+    std::vector<float> W1, b1, W2, b2;
+    int Ntr = 0;
+    std::vector<double> gpX, gpAlpha, gpC2, gpRa, gpRl, gpYm, gpYs;
+    std::vector<double> samp;  // empty: default to tt[0]
+    int P = 0;
+    bool have_layout = false;
+    std::vector<ParamSrc> xsrc;
+    ParamSrc dl{-1, 0, 1e-5}, ts{-1, 0, 0.0}, zsrc{-1, 0, 0.0};
+    int zmode = 0;
+    std::vector<double> zd, zz;
+    int G = 0;
+    bool have_obs = false;
+    std::vector<int> g_nh, g_h, g_off;
+    std::vector<double> o_t, o_m, o_s, g_lim;
+    bool have_sys = false;
+    std::vector<int> sy_mode, sy_nn, sy_off;
+    std::vector<double> sy_budget, sy_t;
+    std::vector<ParamSrc> sy_src;
+    // ---- device state ----
+    bool dirty = true;
+    std::vector<void*> dev_allocs;
+    DevCfg cfg{};
+    bool fused_supported = false;
+    double* coeff_scratch = nullptr;
+    size_t coeff_cap = 0;
+    double* stage_in_dev = nullptr;
+    double* stage_out_dev = nullptr;
+    double* stage_in_host = nullptr;
+    double* stage_out_host = nullptr;
+    size_t stage_cap_in = 0, stage_cap_out = 0;
+    cudaStream_t own_stream = nullptr;
+    // ---- knobs / counters ----
+    int opt_path = 0;
+    long long opt_fused_min = 2048;
+    int opt_max_ctas = 0;
+    int opt_packed = 0;
+    int opt_pt = 0;
+    long long launches = 0;
+    int last_path = 0;
+};
+
+namespace {
+
+int fail(nmma_b200_t* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(h, NMMA_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+bool all_finite(const double* p, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (!std::isfinite(p[i])) return false;
+    return true;
+}
+
+void free_dev(nmma_b200_t* h) {
+    for (void* p : h->dev_allocs) cudaFree(p);
+    h->dev_allocs.clear();
+}
+
+template <typename T>
+int upload(nmma_b200_t* h, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CU(cudaMalloc(&p, bytes + 256));  // slack: 16-byte bulk copies may be rounded up
+    h->dev_allocs.push_back(p);
+    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(p);
+    return NMMA_B200_OK;
+}
+
+int check_src(nmma_b200_t* h, const ParamSrc& s, const char* what) {
+    if (s.col >= h->P) return fail(h, NMMA_B200_ERR_ARG, "%s: column %d out of range (P=%d)", what, s.col, h->P);
+    if (s.xf < 0 || s.xf > 5) return fail(h, NMMA_B200_ERR_ARG, "%s: unknown transform %d", what, s.xf);
+    return NMMA_B200_OK;
+}
+
+ParamSrc to_src(const nmma_b200_param_src& s) { return ParamSrc{s.col, s.transform, s.value}; }
+
+template <int D, int PT, bool PACKED>
+int launch_fused_dk(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
+    constexpr int K = 10;
+    auto kern = fused_mlp_logl_kernel<D, K, PT, PACKED>;
+    const size_t smem = fused_smem_bytes(D, K, h->T);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem));
+    if (per_sm < 1) return fail(h, NMMA_B200_ERR_CUDA, "fused kernel does not fit on an SM (smem %zu B)", smem);
+    const long long tile = (long long)kFusedConsumers * PT;
+    const long long ntiles = (N + tile - 1) / tile;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
+    grid = std::max<long long>(1, std::min(grid, ntiles));
+    kern<<<(unsigned)grid, kFusedThreads, smem, st>>>(h->cfg, pts, N, out);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return NMMA_B200_OK;
+}
+
+template <int D>
+int launch_fused_d(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
+    // points per thread: 2 once there are enough points to keep every SM busy
+    int pt = h->opt_pt;
+    if (pt == 0) pt = (N >= (long long)h->sm_count * kFusedConsumers * 2) ? 2 : 1;
+    if (pt == 1) return launch_fused_dk<D, 1, false>(h, pts, N, out, st);
+    if (h->opt_packed) return launch_fused_dk<D, 2, true>(h, pts, N, out, st);
+    return launch_fused_dk<D, 2, false>(h, pts, N, out, st);
+}
+
+int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
+    switch (h->d) {
+        case 2: return launch_fused_d<2>(h, pts, N, out, st);
+        case 3: return launch_fused_d<3>(h, pts, N, out, st);
+        case 4: return launch_fused_d<4>(h, pts, N, out, st);
+        case 5: return launch_fused_d<5>(h, pts, N, out, st);
+        case 6: return launch_fused_d<6>(h, pts, N, out, st);
+        case 7: return launch_fused_d<7>(h, pts, N, out, st);
+        default: return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused kernel not instantiated for d=%d", h->d);
+    }
+}
+
+bool fused_has(int d, int K) { return d >= 2 && d <= 7 && K == 10; }
+
+int ensure_scratch(nmma_b200_t* h, size_t n_doubles) {
+    if (n_doubles <= h->coeff_cap) return NMMA_B200_OK;
+    if (h->coeff_scratch) cudaFree(h->coeff_scratch);
+    h->coeff_scratch = nullptr;
+    h->coeff_cap = 0;
+    CU(cudaMalloc((void**)&h->coeff_scratch, n_doubles * sizeof(double)));
+    h->coeff_cap = n_doubles;
+    return NMMA_B200_OK;
+}
+
+int launch_frontend(nmma_b200_t* h, const double* pts, long long N, double* coeff, cudaStream_t st) {
+    if (h->kind == 0) {
+        dim3 grid((unsigned)h->F, (unsigned)std::min<long long>(N, 32768));
+        coeff_mlp_kernel<<<grid, kCoeffThreads, 0, st>>>(h->cfg, pts, N, coeff);
+    } else {
+        const long long ntiles = (N + kGpPts - 1) / kGpPts;
+        const size_t smem = (size_t)kGpPts * h->Ntr * sizeof(double);
+        CU(cudaFuncSetAttribute(coeff_gp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ntiles, (long long)h->sm_count * 8));
+        coeff_gp_kernel<<<grid, kGpThreads, smem, st>>>(h->cfg, pts, N, coeff);
+    }
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return NMMA_B200_OK;
+}
+
+// Builds every derived table and uploads the configuration (lazy, after any set_*).
+int finalize(nmma_b200_t* h, bool need_obs) {
+    if (!h->have_svd) return fail(h, NMMA_B200_ERR_STATE, "nmma_b200_set_svd has not been called");
+    if (h->kind < 0) return fail(h, NMMA_B200_ERR_STATE, "no surrogate front end: call nmma_b200_set_mlp or nmma_b200_set_gp");
+    if (!h->have_layout) return fail(h, NMMA_B200_ERR_STATE, "nmma_b200_set_param_layout has not been called");
+    if (need_obs && !h->have_obs) return fail(h, NMMA_B200_ERR_STATE, "nmma_b200_set_observations has not been called");
+    if (!h->dirty) return NMMA_B200_OK;
+    CU(cudaSetDevice(h->device));
+    free_dev(h);
+    const int F = h->F, d = h->d, K = h->K, T = h->T;
+    DevCfg& c = h->cfg;
+    c = DevCfg{};
+    c.F = F; c.d = d; c.K = K; c.T = T; c.P = h->P; c.kind = h->kind;
+
+    if ((int)h->xsrc.size() != d) return fail(h, NMMA_B200_ERR_ARG, "param layout lists %zu model parameters, surrogate has d=%d", h->xsrc.size(), d);
+    for (int i = 0; i < d; ++i) {
+        if (int rc = check_src(h, h->xsrc[i], "model parameter")) return rc;
+        c.xsrc[i] = h->xsrc[i];
+    }
+    if (int rc = check_src(h, h->dl, "luminosity_distance")) return rc;
+    if (int rc = check_src(h, h->ts, "timeshift")) return rc;
+    if (int rc = check_src(h, h->zsrc, "redshift")) return rc;
+    c.dl = h->dl; c.ts = h->ts; c.zsrc = h->zsrc; c.zmode = h->zmode;
+    if (h->zmode == NMMA_B200_Z_TABLE && h->zd.size() < 1)
+        return fail(h, NMMA_B200_ERR_STATE, "z_mode is Z_TABLE but nmma_b200_set_redshift_table has not been called");
+    c.nz = (int)h->zd.size();
+    if (int rc = upload(h, h->zd, &c.zd)) return rc;
+    if (int rc = upload(h, h->zz, &c.zz)) return rc;
+
+    // ---- basis pack + input scaling ----
+    std::vector<double> pden((size_t)F * d), bpack((size_t)F * T * (K + 2));
+    for (size_t i = 0; i < pden.size(); ++i) pden[i] = h->pmax[i] - h->pmin[i];
+    for (int f = 0; f < F; ++f)
+        for (int j = 0; j < T; ++j) {
+            double* r = &bpack[((size_t)f * T + j) * (K + 2)];
+            for (int i = 0; i < K; ++i) r[i] = h->VA[((size_t)f * T + j) * K + i];
+            r[K] = h->maxs[(size_t)f * T + j] - h->mins[(size_t)f * T + j];
+            r[K + 1] = h->mins[(size_t)f * T + j];
+        }
+    if (int rc = upload(h, h->pmin, &c.pmin)) return rc;
+    if (int rc = upload(h, pden, &c.pden)) return rc;
+    if (int rc = upload(h, bpack, &c.bpack)) return rc;
+
+    // ---- stage 1 tables: np.interp(sample_times, tt_f, ., left=inf, right=inf) ----
+    std::vector<double> samp = h->samp;
+    if (samp.empty()) samp.assign(h->tt.begin(), h->tt.begin() + T);
+    const int S = (int)samp.size();
+    c.S = S;
+    for (int s = 0; s < S; ++s) {
+        if (!std::isfinite(samp[s])) return fail(h, NMMA_B200_ERR_ARG, "sample_times[%d] is not finite", s);
+        if (s > 0 && !(samp[s] >= samp[s - 1])) return fail(h, NMMA_B200_ERR_ARG, "sample_times must be non-decreasing");
+    }
+    std::vector<int> s_lo(F), s_hi(F), s1_j((size_t)F * S, 0);
+    std::vector<double> s1_dx((size_t)F * S, 0.0), s1_dt((size_t)F * S, 0.0);
+    bool single = true;
+    int static_fail = 0;
+    for (int f = 0; f < F; ++f) {
+        const double* tf = &h->tt[(size_t)f * T];
+        int lo = S, hi = -1;
+        for (int s = 0; s < S; ++s) {
+            const double x = samp[s];
+            if (x < tf[0] || x > tf[T - 1]) continue;
+            lo = std::min(lo, s); hi = std::max(hi, s);
+            int j = (int)(std::upper_bound(tf, tf + T, x) - tf) - 1;  // last tt[j] <= x
+            const size_t idx = (size_t)f * S + s;
+            s1_j[idx] = j;
+            if (j == T - 1 || tf[j] == x) {
+                s1_dt[idx] = 0.0;
+            } else {
+                s1_dx[idx] = x - tf[j];
+                s1_dt[idx] = tf[j + 1] - tf[j];
+            }
+            if (!(s1_dt[idx] == 0.0 && j == s)) single = false;
+        }
+        if (hi < lo) { lo = 0; hi = -1; }
+        if (!(lo == 0 && hi == S - 1)) single = false;
+        if (hi - lo + 1 < 2) static_fail = 1;
+        s_lo[f] = lo; s_hi[f] = hi;
+    }
+    c.single_stage = single ? 1 : 0;
+    c.static_fail = static_fail;
+    // uniform sample grid -> O(1) interval guess
+    c.uniform = 0;
+    if (S >= 2) {
+        const double ds = (samp[S - 1] - samp[0]) / (S - 1);
+        bool uni = ds > 0;
+        for (int s = 0; s < S && uni; ++s)
+            if (std::fabs(samp[s] - (samp[0] + s * ds)) > 1e-6 * ds) uni = false;
+        if (uni) { c.uniform = 1; c.uni_s0 = samp[0]; c.uni_inv_ds = 1.0 / ds; }
+    }
+    if (int rc = upload(h, samp, &c.samp)) return rc;
+    if (int rc = upload(h, s_lo, &c.s_lo)) return rc;
+    if (int rc = upload(h, s_hi, &c.s_hi)) return rc;
+    if (int rc = upload(h, s1_j, &c.s1_j)) return rc;
+    if (int rc = upload(h, s1_dx, &c.s1_dx)) return rc;
+    if (int rc = upload(h, s1_dt, &c.s1_dt)) return rc;
+
+    // ---- front end ----
+    if (h->kind == 0) {
+        if (h->Kout != K)
+            return fail(h, NMMA_B200_ERR_ARG, "network emits %d coefficients but n_coeff=%d (np.dot(VA[:, :n], cAproj) would not align)", h->Kout, K);
+        const int H = h->H;
+        const int RW = (d + 1 + K + 3) / 4 * 4;
+        const int HP = (H + kHC - 1) / kHC * kHC;
+        c.H = H; c.HP = HP; c.RW = RW;
+        std::vector<float> wpack((size_t)F * HP * RW, 0.f);
+        for (int f = 0; f < F; ++f)
+            for (int j = 0; j < H; ++j) {
+                float* r = &wpack[((size_t)f * HP + j) * RW];
+                for (int i = 0; i < d; ++i) r[i] = h->W1[((size_t)f * d + i) * H + j];
+                r[d] = h->b1[(size_t)f * H + j];
+                for (int k = 0; k < K; ++k) r[d + 1 + k] = h->W2[((size_t)f * H + j) * K + k];
+            }
+        if (int rc = upload(h, wpack, &c.wpack)) return rc;
+        if (int rc = upload(h, h->b2, &c.b2)) return rc;
+    } else {
+        c.Ntr = h->Ntr;
+        // GP inputs are scaled with filter 0's param_mins/maxs: training shares them (em/training.py:216-230)
+        for (int f = 1; f < F; ++f)
+            for (int i = 0; i < d; ++i)
+                if (h->pmin[f * d + i] != h->pmin[i] || h->pmax[f * d + i] != h->pmax[i])
+                    return fail(h, NMMA_B200_ERR_UNSUPPORTED, "GP path needs identical param_mins/maxs across filters");
+        const size_t n = (size_t)F * K;
+        std::vector<double> A(n * h->Ntr), q(n);
+        for (size_t p = 0; p < n; ++p) {
+            q[p] = 1.0 / (2.0 * h->gpRa[p] * h->gpRl[p] * h->gpRl[p]);
+            for (int t = 0; t < h->Ntr; ++t) A[p * h->Ntr + t] = h->gpC2[p] * h->gpAlpha[p * h->Ntr + t];
+        }
+        if (int rc = upload(h, h->gpX, &c.gpX)) return rc;
+        if (int rc = upload(h, A, &c.gpA)) return rc;
+        if (int rc = upload(h, q, &c.gp_q)) return rc;
+        if (int rc = upload(h, h->gpRa, &c.gp_ra)) return rc;
+        if (int rc = upload(h, h->gpYm, &c.gp_ym)) return rc;
+        if (int rc = upload(h, h->gpYs, &c.gp_ys)) return rc;
+    }
+
+    // ---- observations + systematics ----
+    h->fused_supported = false;
+    if (h->have_obs) {
+        const int G = h->G;
+        const int nobs = h->g_off[G];
+        c.G = G; c.nobs = nobs;
+        for (int g = 0; g < G; ++g)
+            for (int k = 0; k < h->g_nh[g]; ++k)
+                if (h->g_h[g * 3 + k] < 0 || h->g_h[g * 3 + k] >= F)
+                    return fail(h, NMMA_B200_ERR_ARG, "observed filter %d maps to model filter %d, but F=%d", g, h->g_h[g * 3 + k], F);
+        std::vector<int> sy_mode = h->sy_mode, sy_nn = h->sy_nn, sy_off = h->sy_off;
+        std::vector<double> sy_budget = h->sy_budget, sy_t = h->sy_t;
+        std::vector<ParamSrc> sy_src = h->sy_src;
+        if (!h->have_sys) {  // FilterSystematicsHandler default: error_budget = 1.0 (systematics.py:203-210)
+            sy_mode.assign(G, 0); sy_nn.assign(G, 0); sy_off.assign(G, 0); sy_budget.assign(G, 1.0);
+            sy_t.clear(); sy_src.clear();
+        } else if ((int)sy_mode.size() != G) {
+            return fail(h, NMMA_B200_ERR_ARG, "systematics describe %zu filters, observations %d", sy_mode.size(), G);
+        }
+        for (auto& s : sy_src)
+            if (int rc = check_src(h, s, "systematics parameter")) return rc;
+        std::vector<int> o_g(nobs);
+        std::vector<double> o_sig(nobs), o_lsc(nobs);
+        for (int g = 0; g < G; ++g)
+            for (int k = h->g_off[g]; k < h->g_off[g + 1]; ++k) {
+                o_g[k] = g;
+                const double sg = std::sqrt(h->o_s[k] * h->o_s[k] + sy_budget[g] * sy_budget[g]);
+                o_sig[k] = sg;
+                o_lsc[k] = std::log(sg) + NMMA_NORM_PDF_LOGC;
+            }
+        std::vector<int> f_goff(F + 1, 0), f_glist;
+        bool direct = true;
+        for (int g = 0; g < G; ++g) direct = direct && (h->g_nh[g] == 1);
+        for (int f = 0; f < F; ++f) {
+            for (int g = 0; g < G; ++g)
+                if (h->g_nh[g] == 1 && h->g_h[g * 3] == f) f_glist.push_back(g);
+            f_goff[f + 1] = (int)f_glist.size();
+        }
+        if (int rc = upload(h, h->g_off, &c.g_off)) return rc;
+        if (int rc = upload(h, h->g_nh, &c.g_nh)) return rc;
+        if (int rc = upload(h, h->g_h, &c.g_h)) return rc;
+        if (int rc = upload(h, h->g_lim, &c.g_lim)) return rc;
+        if (int rc = upload(h, o_g, &c.o_g)) return rc;
+        if (int rc = upload(h, h->o_t, &c.o_t)) return rc;
+        if (int rc = upload(h, h->o_m, &c.o_m)) return rc;
+        if (int rc = upload(h, h->o_s, &c.o_s)) return rc;
+        if (int rc = upload(h, o_sig, &c.o_sig)) return rc;
+        if (int rc = upload(h, o_lsc, &c.o_lsc)) return rc;
+        if (int rc = upload(h, sy_mode, &c.sy_mode)) return rc;
+        if (int rc = upload(h, sy_budget, &c.sy_budget)) return rc;
+        if (int rc = upload(h, sy_nn, &c.sy_nn)) return rc;
+        if (int rc = upload(h, sy_off, &c.sy_off)) return rc;
+        if (int rc = upload(h, sy_src, &c.sy_src)) return rc;
+        if (int rc = upload(h, sy_t, &c.sy_t)) return rc;
+        if (int rc = upload(h, f_goff, &c.f_goff)) return rc;
+        if (int rc = upload(h, f_glist, &c.f_glist)) return rc;
+        h->fused_supported = (h->kind == 0) && direct && fused_has(d, K) &&
+                             fused_smem_bytes(d, K, T) <= 227 * 1024;
+    }
+    h->dirty = false;
+    return NMMA_B200_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int nmma_b200_version(void) { return kVersion; }
+
+const char* nmma_b200_last_error(const nmma_b200_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int nmma_b200_create(int device, nmma_b200_t** out) {
+    nmma_b200_t* h = nullptr;
+    if (!out) return fail(nullptr, NMMA_B200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, NMMA_B200_ERR_CUDA, "no CUDA device available (%s); nmma_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(nullptr, NMMA_B200_ERR_ARG, "device %d out of range (have %d)", device, count);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, NMMA_B200_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, NMMA_B200_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    device, prop.major, prop.minor);
+    h = new nmma_b200_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, NMMA_B200_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_destroy(nmma_b200_t* h) {
+    if (!h) return NMMA_B200_OK;
+    cudaSetDevice(h->device);
+    free_dev(h);
+    if (h->coeff_scratch) cudaFree(h->coeff_scratch);
+    if (h->stage_in_dev) cudaFree(h->stage_in_dev);
+    if (h->stage_out_dev) cudaFree(h->stage_out_dev);
+    if (h->stage_in_host) cudaFreeHost(h->stage_in_host);
+    if (h->stage_out_host) cudaFreeHost(h->stage_out_host);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_svd(nmma_b200_t* h, int F, int d, int K, int T, const double* tt, const double* param_mins,
+                      const double* param_maxs, const double* VA, const double* mins, const double* maxs) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (F < 1 || d < 1 || K < 1 || T < 2) return fail(h, NMMA_B200_ERR_ARG, "set_svd: need F>=1, d>=1, K>=1, T>=2");
+    if (d > kMaxD || K > kMaxK) return fail(h, NMMA_B200_ERR_UNSUPPORTED, "set_svd: d<=%d and K<=%d supported", kMaxD, kMaxK);
+    if (!tt || !param_mins || !param_maxs || !VA || !mins || !maxs) return fail(h, NMMA_B200_ERR_ARG, "set_svd: NULL array");
+    const size_t FT = (size_t)F * T;
+    if (!all_finite(tt, FT) || !all_finite(VA, FT * K) || !all_finite(mins, FT) || !all_finite(maxs, FT) ||
+        !all_finite(param_mins, (size_t)F * d) || !all_finite(param_maxs, (size_t)F * d))
+        return fail(h, NMMA_B200_ERR_UNSUPPORTED, "set_svd: non-finite entries in the SVD model are not supported");
+    for (int f = 0; f < F; ++f)
+        for (int j = 1; j < T; ++j)
+            if (!(tt[(size_t)f * T + j] > tt[(size_t)f * T + j - 1]))
+                return fail(h, NMMA_B200_ERR_ARG, "set_svd: tt must be strictly increasing (filter %d, node %d)", f, j);
+    h->F = F; h->d = d; h->K = K; h->T = T;
+    h->tt.assign(tt, tt + FT);
+    h->pmin.assign(param_mins, param_mins + (size_t)F * d);
+    h->pmax.assign(param_maxs, param_maxs + (size_t)F * d);
+    h->VA.assign(VA, VA + FT * K);
+    h->mins.assign(mins, mins + FT);
+    h->maxs.assign(maxs, maxs + FT);
+    h->have_svd = true;
+    h->kind = -1;
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_mlp(nmma_b200_t* h, int H, int K_out, const float* W1, const float* b1, const float* W2, const float* b2) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (!h->have_svd) return fail(h, NMMA_B200_ERR_STATE, "set_mlp: call nmma_b200_set_svd first");
+    if (H < 1 || K_out < 1 || K_out > kMaxK) return fail(h, NMMA_B200_ERR_ARG, "set_mlp: bad H=%d / K_out=%d", H, K_out);
+    if (!W1 || !b1 || !W2 || !b2) return fail(h, NMMA_B200_ERR_ARG, "set_mlp: NULL array");
+    const size_t F = h->F, d = h->d;
+    h->H = H; h->Kout = K_out;
+    h->W1.assign(W1, W1 + F * d * H);
+    h->b1.assign(b1, b1 + F * H);
+    h->W2.assign(W2, W2 + F * H * K_out);
+    h->b2.assign(b2, b2 + F * K_out);
+    h->kind = 0;
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_gp(nmma_b200_t* h, int Ntr, const double* X, const double* alpha, const double* c2,
+                     const double* rq_alpha, const double* rq_len, const double* ymean, const double* ystd) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (!h->have_svd) return fail(h, NMMA_B200_ERR_STATE, "set_gp: call nmma_b200_set_svd first");
+    if (Ntr < 1) return fail(h, NMMA_B200_ERR_ARG, "set_gp: Ntr must be positive");
+    if (!X || !alpha || !c2 || !rq_alpha || !rq_len || !ymean || !ystd) return fail(h, NMMA_B200_ERR_ARG, "set_gp: NULL array");
+    if ((size_t)kGpPts * Ntr * sizeof(double) > 200 * 1024)
+        return fail(h, NMMA_B200_ERR_UNSUPPORTED, "set_gp: Ntr=%d exceeds the shared-memory tile (max %d)", Ntr, (int)(200 * 1024 / (kGpPts * 8)));
+    const size_t n = (size_t)h->F * h->K;
+    h->Ntr = Ntr;
+    h->gpX.assign(X, X + (size_t)Ntr * h->d);
+    h->gpAlpha.assign(alpha, alpha + n * Ntr);
+    h->gpC2.assign(c2, c2 + n);
+    h->gpRa.assign(rq_alpha, rq_alpha + n);
+    h->gpRl.assign(rq_len, rq_len + n);
+    h->gpYm.assign(ymean, ymean + n);
+    h->gpYs.assign(ystd, ystd + n);
+    h->kind = 1;
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_sample_grid(nmma_b200_t* h, int S, const double* sample_times) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (S < 0) return fail(h, NMMA_B200_ERR_ARG, "set_sample_grid: S < 0");
+    if (S == 0 || !sample_times) h->samp.clear();
+    else h->samp.assign(sample_times, sample_times + S);
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_param_layout(nmma_b200_t* h, int P, const nmma_b200_param_src* model_params,
+                               nmma_b200_param_src luminosity_distance, nmma_b200_param_src timeshift,
+                               nmma_b200_param_src redshift, int z_mode) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (!h->have_svd) return fail(h, NMMA_B200_ERR_STATE, "set_param_layout: call nmma_b200_set_svd first");
+    if (P < 1 || !model_params) return fail(h, NMMA_B200_ERR_ARG, "set_param_layout: P < 1 or NULL model_params");
+    if (z_mode < 0 || z_mode > 2) return fail(h, NMMA_B200_ERR_ARG, "set_param_layout: unknown z_mode %d", z_mode);
+    h->P = P;
+    h->xsrc.clear();
+    for (int i = 0; i < h->d; ++i) h->xsrc.push_back(to_src(model_params[i]));
+    h->dl = to_src(luminosity_distance);
+    h->ts = to_src(timeshift);
+    h->zsrc = to_src(redshift);
+    h->zmode = z_mode;
+    h->have_layout = true;
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_redshift_table(nmma_b200_t* h, int n, const double* dist_grid, const double* z_grid) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (n < 0 || (n > 0 && (!dist_grid || !z_grid))) return fail(h, NMMA_B200_ERR_ARG, "set_redshift_table: bad arguments");
+    for (int i = 1; i < n; ++i)
+        if (!(dist_grid[i] >= dist_grid[i - 1])) return fail(h, NMMA_B200_ERR_ARG, "set_redshift_table: dist_grid must be sorted");
+    h->zd.assign(dist_grid, dist_grid + n);
+    h->zz.assign(z_grid, z_grid + n);
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_observations(nmma_b200_t* h, int G, const int32_t* n_helpers, const int32_t* helper_idx,
+                               const int32_t* offsets, const double* t, const double* mag, const double* sigma_obs,
+                               const double* det_limit) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (G < 1 || !n_helpers || !helper_idx || !offsets || !t || !mag || !sigma_obs || !det_limit)
+        return fail(h, NMMA_B200_ERR_ARG, "set_observations: bad arguments");
+    if (offsets[0] != 0) return fail(h, NMMA_B200_ERR_ARG, "set_observations: offsets[0] must be 0");
+    for (int g = 0; g < G; ++g) {
+        if (offsets[g + 1] < offsets[g]) return fail(h, NMMA_B200_ERR_ARG, "set_observations: offsets must be non-decreasing");
+        if (n_helpers[g] < 1 || n_helpers[g] > NMMA_B200_MAX_HELPERS)
+            return fail(h, NMMA_B200_ERR_ARG, "set_observations: n_helpers[%d]=%d outside 1..3", g, n_helpers[g]);
+    }
+    const int n = offsets[G];
+    for (int k = 0; k < n; ++k)
+        if (!std::isfinite(t[k])) return fail(h, NMMA_B200_ERR_ARG, "set_observations: observation time %d is not finite", k);
+    h->G = G;
+    h->g_nh.assign(n_helpers, n_helpers + G);
+    h->g_h.assign(helper_idx, helper_idx + (size_t)G * 3);
+    h->g_off.assign(offsets, offsets + G + 1);
+    h->o_t.assign(t, t + n);
+    h->o_m.assign(mag, mag + n);
+    h->o_s.assign(sigma_obs, sigma_obs + n);
+    h->g_lim.assign(det_limit, det_limit + G);
+    h->have_obs = true;
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_systematics(nmma_b200_t* h, int G, const int32_t* mode, const double* budget,
+                              const int32_t* n_nodes, const int32_t* node_offset,
+                              const nmma_b200_param_src* node_src, const double* node_times) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (G < 1 || !mode || !budget || !n_nodes || !node_offset) return fail(h, NMMA_B200_ERR_ARG, "set_systematics: bad arguments");
+    int total = 0;
+    for (int g = 0; g < G; ++g) {
+        if (mode[g] < 0 || mode[g] > 2) return fail(h, NMMA_B200_ERR_ARG, "set_systematics: unknown mode %d", mode[g]);
+        const int nn = mode[g] == 0 ? 0 : (mode[g] == 1 ? 1 : n_nodes[g]);
+        if (mode[g] == 2 && (nn < 1 || nn > kMaxSysNodes))
+            return fail(h, NMMA_B200_ERR_UNSUPPORTED, "set_systematics: %d time nodes (1..%d supported)", nn, kMaxSysNodes);
+        if (nn > 0) total = std::max(total, node_offset[g] + nn);
+    }
+    if (total > 0 && (!node_src || !node_times)) return fail(h, NMMA_B200_ERR_ARG, "set_systematics: NULL node arrays");
+    h->sy_mode.assign(mode, mode + G);
+    h->sy_budget.assign(budget, budget + G);
+    h->sy_nn.assign(n_nodes, n_nodes + G);
+    h->sy_off.assign(node_offset, node_offset + G);
+    h->sy_src.clear();
+    for (int i = 0; i < total; ++i) h->sy_src.push_back(to_src(node_src[i]));
+    h->sy_t.assign(node_times, node_times + total);
+    h->have_sys = true;
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* out_dev, void* stream) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "logl: N < 0");
+    if (int rc = finalize(h, true)) return rc;
+    if (N == 0) return NMMA_B200_OK;
+    if (!points_dev || !out_dev) return fail(h, NMMA_B200_ERR_ARG, "logl: NULL device pointer");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int path = h->opt_path;
+    if (path == 1 && !h->fused_supported)
+        return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused kernel unavailable for this configuration (GP path, averaged filters, or d/K not instantiated)");
+    if (path == 0) path = (h->fused_supported && N >= h->opt_fused_min) ? 1 : 2;
+    h->last_path = path;
+    if (path == 1) return launch_fused(h, points_dev, N, out_dev, st);
+    const size_t FK = (size_t)h->F * h->K;
+    const long long chunk = std::min<long long>(N, kTwoStageChunk);
+    if (int rc = ensure_scratch(h, (size_t)chunk * FK)) return rc;
+    for (long long n0 = 0; n0 < N; n0 += chunk) {
+        const long long nn = std::min<long long>(chunk, N - n0);
+        const double* pts = points_dev + n0 * h->P;
+        if (int rc = launch_frontend(h, pts, nn, h->coeff_scratch, st)) return rc;
+        const long long warps_per_block = kBackThreads / 32;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nn + warps_per_block - 1) / warps_per_block, (long long)h->sm_count * 16));
+        backend_logl_kernel<<<grid, kBackThreads, 0, st>>>(h->cfg, pts, h->coeff_scratch, nn, out_dev + n0);
+        CU(cudaGetLastError());
+        h->launches += 1;
+    }
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "logl_host: N < 0");
+    if (int rc = finalize(h, true)) return rc;
+    if (N == 0) return NMMA_B200_OK;
+    if (!points_host || !out_host) return fail(h, NMMA_B200_ERR_ARG, "logl_host: NULL pointer");
+    CU(cudaSetDevice(h->device));
+    const size_t nin = (size_t)N * h->P, nout = (size_t)N;
+    if (nin > h->stage_cap_in) {
+        if (h->stage_in_dev) cudaFree(h->stage_in_dev);
+        if (h->stage_in_host) cudaFreeHost(h->stage_in_host);
+        h->stage_in_dev = nullptr; h->stage_in_host = nullptr; h->stage_cap_in = 0;
+        CU(cudaMalloc((void**)&h->stage_in_dev, nin * sizeof(double)));
+        CU(cudaMallocHost((void**)&h->stage_in_host, nin * sizeof(double)));
+        h->stage_cap_in = nin;
+    }
+    if (nout > h->stage_cap_out) {
+        if (h->stage_out_dev) cudaFree(h->stage_out_dev);
+        if (h->stage_out_host) cudaFreeHost(h->stage_out_host);
+        h->stage_out_dev = nullptr; h->stage_out_host = nullptr; h->stage_cap_out = 0;
+        CU(cudaMalloc((void**)&h->stage_out_dev, nout * sizeof(double)));
+        CU(cudaMallocHost((void**)&h->stage_out_host, nout * sizeof(double)));
+        h->stage_cap_out = nout;
+    }
+    std::memcpy(h->stage_in_host, points_host, nin * sizeof(double));
+    CU(cudaMemcpyAsync(h->stage_in_dev, h->stage_in_host, nin * sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
+    if (int rc = nmma_b200_logl(h, h->stage_in_dev, N, h->stage_out_dev, h->own_stream)) return rc;
+    CU(cudaMemcpyAsync(h->stage_out_host, h->stage_out_dev, nout * sizeof(double), cudaMemcpyDeviceToHost, h->own_stream));
+    CU(cudaStreamSynchronize(h->own_stream));
+    std::memcpy(out_host, h->stage_out_host, nout * sizeof(double));
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_coeffs(nmma_b200_t* h, const double* points_dev, int64_t N, double* coeffs_dev, void* stream) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "coeffs: N < 0");
+    if (int rc = finalize(h, false)) return rc;
+    if (N == 0) return NMMA_B200_OK;
+    if (!points_dev || !coeffs_dev) return fail(h, NMMA_B200_ERR_ARG, "coeffs: NULL device pointer");
+    CU(cudaSetDevice(h->device));
+    return launch_frontend(h, points_dev, N, coeffs_dev, static_cast<cudaStream_t>(stream));
+}
+
+int nmma_b200_mags(nmma_b200_t* h, const double* points_dev, int64_t N, int apparent, double* mags_dev,
+                   double* tobs_dev, void* stream) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "mags: N < 0");
+    if (int rc = finalize(h, false)) return rc;
+    if (N == 0) return NMMA_B200_OK;
+    if (!points_dev || !mags_dev) return fail(h, NMMA_B200_ERR_ARG, "mags: NULL device pointer");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t FK = (size_t)h->F * h->K;
+    const long long chunk = std::min<long long>(N, kTwoStageChunk);
+    if (int rc = ensure_scratch(h, (size_t)chunk * FK)) return rc;
+    const int S = h->cfg.S;
+    for (long long n0 = 0; n0 < N; n0 += chunk) {
+        const long long nn = std::min<long long>(chunk, N - n0);
+        const double* pts = points_dev + n0 * h->P;
+        if (int rc = launch_frontend(h, pts, nn, h->coeff_scratch, st)) return rc;
+        const long long total = nn * h->F * S;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)h->sm_count * 32));
+        backend_mags_kernel<<<grid, 256, 0, st>>>(h->cfg, pts, h->coeff_scratch, nn, apparent,
+                                                  mags_dev + (size_t)n0 * h->F * S,
+                                                  tobs_dev ? tobs_dev + (size_t)n0 * S : nullptr);
+        CU(cudaGetLastError());
+        h->launches += 1;
+    }
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
+    if (!h || !key) return NMMA_B200_ERR_ARG;
+    const std::string k(key);
+    if (k == "path") { if (value < 0 || value > 2) return fail(h, NMMA_B200_ERR_ARG, "path must be 0, 1 or 2"); h->opt_path = (int)value; }
+    else if (k == "fused_min_points") h->opt_fused_min = value;
+    else if (k == "max_ctas") h->opt_max_ctas = (int)value;
+    else if (k == "packed_fma") h->opt_packed = value ? 1 : 0;
+    else if (k == "points_per_thread") { if (value < 0 || value > 2) return fail(h, NMMA_B200_ERR_ARG, "points_per_thread must be 0 (auto), 1 or 2"); h->opt_pt = (int)value; }
+    else return fail(h, NMMA_B200_ERR_ARG, "unknown option '%s'", key);
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
+    if (!h || !key || !value) return NMMA_B200_ERR_ARG;
+    const std::string k(key);
+    if (k == "launches") *value = h->launches;
+    else if (k == "last_path") *value = h->last_path;
+    else if (k == "sm_count") *value = h->sm_count;
+    else if (k == "fused_supported") { if (int rc = finalize(h, true)) return rc; *value = h->fused_supported ? 1 : 0; }
+    else if (k == "algorithmic_flop_per_eval") {
+        // F * [2 H (d + K) + 2 T K] (MLP) or Ntr*3d + F*K*Ntr*8 + F*2*T*K (GP)
+        if (h->kind == 0) *value = (int64_t)h->F * (2LL * h->H * (h->d + h->K) + 2LL * h->T * h->K);
+        else if (h->kind == 1) *value = (int64_t)h->Ntr * 3 * h->d + (int64_t)h->F * h->K * h->Ntr * 8 + (int64_t)h->F * 2 * h->T * h->K;
+        else return fail(h, NMMA_B200_ERR_STATE, "no surrogate configured");
+    } else return fail(h, NMMA_B200_ERR_ARG, "unknown info key '%s'", key);
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_ffma_peak(nmma_b200_t* h, int variant, int iters, double* flops_per_s) {
+    if (!h || !flops_per_s || iters < 1) return NMMA_B200_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    float* sink = nullptr;
+    CU(cudaMalloc((void**)&sink, sizeof(float)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const unsigned grid = (unsigned)h->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0, h->own_stream));
+        if (variant == 1) ffma_peak_kernel<true><<<grid, 256, 0, h->own_stream>>>(iters, 1.0f, sink);
+        else ffma_peak_kernel<false><<<grid, 256, 0, h->own_stream>>>(iters, 1.0f, sink);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e1, h->own_stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        h->launches += 1;
+        const double fl = 2.0 * 16.0 * (double)iters * 256.0 * grid;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *flops_per_s = best;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_obs_terms(nmma_b200_t* h, int n, const double* mag, const double* model_mag, const double* sigma_obs,
+                        const double* sigma_sys, const double* det_limit, double* out) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (n < 0 || (n > 0 && (!mag || !model_mag || !sigma_obs || !sigma_sys || !det_limit || !out)))
+        return fail(h, NMMA_B200_ERR_ARG, "obs_terms: bad arguments");
+    if (n == 0) return NMMA_B200_OK;
+    CU(cudaSetDevice(h->device));
+    double* buf = nullptr;
+    const size_t nb = (size_t)n * sizeof(double);
+    CU(cudaMalloc((void**)&buf, 6 * nb));
+    const double* src[5] = {mag, model_mag, sigma_obs, sigma_sys, det_limit};
+    for (int i = 0; i < 5; ++i) {
+        cudaError_t e = cudaMemcpy(buf + (size_t)i * n, src[i], nb, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(buf); return fail(h, NMMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e)); }
+    }
+    obs_terms_kernel<<<(n + 255) / 256, 256, 0, h->own_stream>>>(n, buf, buf + n, buf + 2 * (size_t)n, buf + 3 * (size_t)n,
+                                                                buf + 4 * (size_t)n, buf + 5 * (size_t)n);
+    h->launches += 1;
+    cudaError_t e = cudaStreamSynchronize(h->own_stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, buf + 5 * (size_t)n, nb, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(h, NMMA_B200_ERR_CUDA, "obs_terms: %s", cudaGetErrorString(e));
+    return NMMA_B200_OK;
+}
+
+}  // extern "C"

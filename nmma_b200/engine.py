@@ -1,0 +1,238 @@
+"""Thin Python owner of one ``nmma_b200_t`` handle.
+
+PyTorch is plumbing only: it provides device buffers and the current CUDA
+stream; every computation happens inside ``libnmma_b200.so`` behind the C ABI
+(``include/nmma_b200.h``).  There is no CPU fallback -- constructing an engine
+without the built library or without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import ParamSrc
+
+SENTINEL = -1.7976931348623157e308  # np.nan_to_num(-np.inf), nmma/core/base.py:82
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class KilonovaEngine:
+    """Device-resident surrogate + observation tables and the kernels that use them."""
+
+    def __init__(self, device: int = 0):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        rc = self._lib.nmma_b200_create(int(device), C.byref(self._h))
+        if rc != L.OK:
+            msg = self._lib.nmma_b200_last_error(None).decode()
+            self._h = None
+            raise L.NmmaB200Error(rc, msg)
+        self.device = int(device)
+        self.F = self.d = self.K = self.T = self.P = self.S = 0
+
+    # ---- lifetime -------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nmma_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != L.OK:
+            raise L.NmmaB200Error(rc, self._lib.nmma_b200_last_error(self._h).decode())
+
+    # ---- staging ---------------------------------------------------------------------
+    def set_surrogate(self, sw):
+        """Stage a :class:`nmma_b200.mlmodel.SurrogateWeights` (replaces load_filt_model)."""
+        F, d, K, T = sw.F, sw.d, sw.n_coeff, sw.T
+        tt, pm, pM = _f64(sw.tt), _f64(sw.param_mins), _f64(sw.param_maxs)
+        VA, mins, maxs = _f64(sw.VA), _f64(sw.mins), _f64(sw.maxs)
+        assert VA.shape == (F, T, K) and tt.shape == (F, T) and pm.shape == (F, d)
+        self._check(self._lib.nmma_b200_set_svd(self._h, F, d, K, T, _dptr(tt), _dptr(pm), _dptr(pM),
+                                                _dptr(VA), _dptr(mins), _dptr(maxs)))
+        if sw.kind == "mlp":
+            W1 = np.ascontiguousarray(sw.W1, np.float32)
+            b1 = np.ascontiguousarray(sw.b1, np.float32)
+            W2 = np.ascontiguousarray(sw.W2, np.float32)
+            b2 = np.ascontiguousarray(sw.b2, np.float32)
+            H, Kout = W1.shape[2], W2.shape[2]
+            assert W1.shape == (F, d, H) and W2.shape == (F, H, Kout)
+            self._check(self._lib.nmma_b200_set_mlp(self._h, H, Kout, _fptr(W1), _fptr(b1), _fptr(W2), _fptr(b2)))
+        elif sw.kind == "gp":
+            X, al = _f64(sw.X), _f64(sw.alpha)
+            Ntr = X.shape[0]
+            assert al.shape == (F, K, Ntr)
+            arrs = [_f64(getattr(sw, n)) for n in ("c2", "rq_alpha", "rq_len", "ymean", "ystd")]
+            self._check(self._lib.nmma_b200_set_gp(self._h, Ntr, _dptr(X), _dptr(al), *[_dptr(a) for a in arrs]))
+        else:
+            raise ValueError(sw.kind)
+        self.F, self.d, self.K, self.T = F, d, K, T
+        self.S = T
+
+    def set_sample_grid(self, sample_times: Optional[Sequence[float]]):
+        if sample_times is None:
+            self._check(self._lib.nmma_b200_set_sample_grid(self._h, 0, None))
+            self.S = self.T
+        else:
+            st = _f64(sample_times)
+            self._check(self._lib.nmma_b200_set_sample_grid(self._h, st.size, _dptr(st)))
+            self.S = int(st.size)
+
+    def set_param_layout(self, P: int, model_params: Sequence[ParamSrc], luminosity_distance: ParamSrc = None,
+                         timeshift: ParamSrc = None, redshift: ParamSrc = None, z_mode: int = L.Z_ZERO):
+        arr = (ParamSrc * len(model_params))(*model_params)
+        dl = luminosity_distance if luminosity_distance is not None else ParamSrc.const(1e-5)
+        ts = timeshift if timeshift is not None else ParamSrc.const(0.0)
+        zs = redshift if redshift is not None else ParamSrc.const(0.0)
+        self._check(self._lib.nmma_b200_set_param_layout(self._h, int(P), arr, dl, ts, zs, int(z_mode)))
+        self.P = int(P)
+
+    def set_redshift_table(self, dist_grid, z_grid):
+        dg, zg = _f64(dist_grid), _f64(z_grid)
+        assert dg.shape == zg.shape
+        self._check(self._lib.nmma_b200_set_redshift_table(self._h, dg.size, _dptr(dg), _dptr(zg)))
+
+    def set_observations(self, helper_lists, times, mags, sigmas, det_limits):
+        """``helper_lists[g]``: model-filter indices of observed filter g (1..3);
+        ``times/mags/sigmas[g]``: arrays of that filter; ``det_limits[g]``: float."""
+        G = len(helper_lists)
+        nh = np.array([len(h) for h in helper_lists], np.int32)
+        hidx = np.zeros((G, 3), np.int32)
+        for g, h in enumerate(helper_lists):
+            hidx[g, :len(h)] = h
+        off = np.zeros(G + 1, np.int32)
+        off[1:] = np.cumsum([len(t) for t in times])
+        cat = lambda xs: _f64(np.concatenate([np.asarray(x, float).ravel() for x in xs])) if off[-1] else np.zeros(0)
+        t, m, s = cat(times), cat(mags), cat(sigmas)
+        lim = _f64(det_limits)
+        self._check(self._lib.nmma_b200_set_observations(self._h, G, _iptr(nh), _iptr(hidx), _iptr(off),
+                                                         _dptr(t), _dptr(m), _dptr(s), _dptr(lim)))
+        self.G = G
+
+    def set_systematics(self, modes, budgets, node_srcs, node_times):
+        """Per observed filter g: ``modes[g]`` in SYS_*, ``budgets[g]`` float,
+        ``node_srcs[g]`` list of ParamSrc, ``node_times[g]`` list of float (SYS_INTERP)."""
+        G = len(modes)
+        mode = np.asarray(modes, np.int32)
+        bud = _f64(budgets)
+        nn = np.array([len(s) for s in node_srcs], np.int32)
+        off = np.zeros(G, np.int32)
+        off[1:] = np.cumsum(nn)[:-1]
+        flat = [s for lst in node_srcs for s in lst]
+        src = (ParamSrc * max(len(flat), 1))(*flat)
+        times = []
+        for g in range(G):
+            tg = list(node_times[g]) if node_times[g] is not None else []
+            tg = tg + [0.0] * (nn[g] - len(tg))
+            times.extend(tg)
+        nt = _f64(times if times else [0.0])
+        self._check(self._lib.nmma_b200_set_systematics(self._h, G, _iptr(mode), _dptr(bud), _iptr(nn), _iptr(off),
+                                                        src, _dptr(nt)))
+
+    # ---- compute ----------------------------------------------------------------------
+    @staticmethod
+    def _stream():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _as_device_points(self, points):
+        import torch
+        if isinstance(points, torch.Tensor):
+            if not points.is_cuda:
+                raise ValueError("tensor points must live on the GPU; pass a NumPy array for host data")
+            pts = points.to(dtype=torch.float64).contiguous()
+        else:
+            pts = torch.from_numpy(_f64(points)).to(f"cuda:{self.device}")
+        if pts.ndim != 2 or pts.shape[1] != self.P:
+            raise ValueError(f"points must have shape [N, {self.P}], got {tuple(pts.shape)}")
+        return pts
+
+    def logl_device(self, points, out=None):
+        """log L for a CUDA tensor ``points[N,P]``; returns a CUDA float64 tensor (async on the current stream)."""
+        import torch
+        pts = self._as_device_points(points)
+        N = pts.shape[0]
+        if out is None:
+            out = torch.empty(N, dtype=torch.float64, device=pts.device)
+        with torch.cuda.device(pts.device):
+            self._check(self._lib.nmma_b200_logl(self._h, C.c_void_p(pts.data_ptr()), N,
+                                                 C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def logl_host(self, points) -> np.ndarray:
+        """log L for host ``points[N,P]`` through ``nmma_b200_logl_host`` (H2D + kernels + D2H)."""
+        pts = _f64(points)
+        if pts.ndim == 1:
+            pts = pts[None, :]
+        if pts.shape[1] != self.P:
+            raise ValueError(f"points must have shape [N, {self.P}], got {pts.shape}")
+        out = np.empty(pts.shape[0], np.float64)
+        self._check(self._lib.nmma_b200_logl_host(self._h, _dptr(pts), pts.shape[0], _dptr(out)))
+        return out
+
+    def mags(self, points, apparent: bool = False):
+        """(mags[N,F,S], tobs[N,S]) CUDA tensors: generate_lightcurve / gen_detector_lc."""
+        import torch
+        pts = self._as_device_points(points)
+        N = pts.shape[0]
+        mags = torch.empty((N, self.F, self.S), dtype=torch.float64, device=pts.device)
+        tobs = torch.empty((N, self.S), dtype=torch.float64, device=pts.device)
+        with torch.cuda.device(pts.device):
+            self._check(self._lib.nmma_b200_mags(self._h, C.c_void_p(pts.data_ptr()), N, int(bool(apparent)),
+                                                 C.c_void_p(mags.data_ptr()), C.c_void_p(tobs.data_ptr()),
+                                                 self._stream()))
+        return mags, tobs
+
+    def coeffs(self, points):
+        import torch
+        pts = self._as_device_points(points)
+        N = pts.shape[0]
+        out = torch.empty((N, self.F, self.K), dtype=torch.float64, device=pts.device)
+        with torch.cuda.device(pts.device):
+            self._check(self._lib.nmma_b200_coeffs(self._h, C.c_void_p(pts.data_ptr()), N,
+                                                   C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def obs_terms(self, mag, model_mag, sigma_obs, sigma_sys, det_limit) -> np.ndarray:
+        arrs = np.broadcast_arrays(*[np.asarray(a, float) for a in (mag, model_mag, sigma_obs, sigma_sys, det_limit)])
+        arrs = [_f64(a).ravel() for a in arrs]
+        out = np.empty(arrs[0].size, np.float64)
+        self._check(self._lib.nmma_b200_obs_terms(self._h, out.size, *[_dptr(a) for a in arrs], _dptr(out)))
+        return out
+
+    # ---- knobs -------------------------------------------------------------------------
+    def set_option(self, key: str, value: int):
+        self._check(self._lib.nmma_b200_set_option(self._h, key.encode(), int(value)))
+
+    def get_info(self, key: str) -> int:
+        v = C.c_int64()
+        self._check(self._lib.nmma_b200_get_info(self._h, key.encode(), C.byref(v)))
+        return int(v.value)
+
+    def ffma_peak(self, variant: int = 0, iters: int = 20000) -> float:
+        v = C.c_double()
+        self._check(self._lib.nmma_b200_ffma_peak(self._h, int(variant), int(iters), C.byref(v)))
+        return float(v.value)

@@ -1,0 +1,113 @@
+"""Shared builders for the parity tests: one in-memory configuration -> GPU likelihood + oracle."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+SENTINEL = -1.7976931348623157e308
+
+
+def fixture_core(kind="mlp", filters=("ztfr", "sdssu", "2massks")):
+    """Bu2019nsbh fixture weights (tests/golden/bu2019nsbh_fixture.npz) in the reference's in-memory layout."""
+    z = np.load(os.path.join(GOLDEN, "bu2019nsbh_fixture.npz"))
+    core = {}
+    for f in filters:
+        key = f.replace(":", "_")
+        T = z[f"{key}/VA"].shape[0]
+        VA = np.zeros((T, T))
+        VA[:, :10] = z[f"{key}/VA"]
+        entry = dict(VA=VA, mins=z[f"{key}/mins"], maxs=z[f"{key}/maxs"], tt=z[f"{key}/tt"],
+                     param_mins=z[f"{key}/param_mins"], param_maxs=z[f"{key}/param_maxs"], n_coeff=10)
+        if kind == "mlp":
+            entry["model"] = tuple(z[f"{key}/{n}"] for n in ("W1", "b1", "W2", "b2"))
+        else:
+            entry["gps"] = {k: z[f"ztfr/gp_{k}"] for k in ("X", "alpha", "c2", "rq_alpha", "rq_len", "ymean", "ystd")}
+        core[f] = entry
+    return core
+
+
+class UnpackedGP:
+    """Oracle-side stand-in for a fitted sklearn GaussianProcessRegressor rebuilt from unpacked arrays:
+    ``predict`` follows sklearn's ``kernel_(X, X_train_) @ alpha_`` with RationalQuadratic.__call__
+    (cdist(X/l, Y/l, 'sqeuclidean'); base = 1 + d/(2 alpha); K = C^2 * base**-alpha)."""
+
+    def __init__(self, X, alpha, c2, ra, rl, ym, ys):
+        self.X, self.alpha, self.c2, self.ra, self.rl, self.ym, self.ys = X, alpha, c2, ra, rl, ym, ys
+
+    def predict(self, x, return_std=False):
+        from scipy.spatial.distance import cdist
+        d = cdist(np.atleast_2d(x) / self.rl, self.X / self.rl, metric="sqeuclidean")
+        K = self.c2 * (1 + d / (2 * self.ra)) ** (-self.ra)
+        y = self.ys * (K @ self.alpha) + self.ym
+        return (y, np.zeros_like(y)) if return_std else y
+
+
+def oracle_ready_core(core):
+    """Replace unpacked GP dicts by objects with a ``predict`` method for the oracle."""
+    out = {}
+    for f, e in core.items():
+        e = dict(e)
+        if isinstance(e.get("gps"), dict):
+            g = e["gps"]
+            e["gps"] = [UnpackedGP(g["X"], g["alpha"][i], g["c2"][i], g["rq_alpha"][i], g["rq_len"][i],
+                                   g["ymean"][i], g["ystd"][i]) for i in range(g["alpha"].shape[0])]
+        out[f] = e
+    return out
+
+
+def synthetic_observations(filters, rng, n_per_filter=8, tmin=0.3, tmax=12.0, n_ul=1, mag0=18.0):
+    """(times{f}, mags{f}, errs{f}, trigger) relative to trigger, with `n_ul` upper limits per filter."""
+    times, mags, errs = {}, {}, {}
+    for f in filters:
+        n = int(n_per_filter if np.isscalar(n_per_filter) else n_per_filter[f])
+        t = np.sort(rng.uniform(tmin, tmax, n))
+        m = mag0 + 0.4 * t + rng.normal(scale=0.3, size=n)
+        e = rng.uniform(0.02, 0.3, n)
+        idx = rng.choice(n, size=min(n_ul, n), replace=False) if n_ul else []
+        for i in idx:
+            e[i] = np.inf
+        times[f], mags[f], errs[f] = t, m, e
+    return times, mags, errs, 0.0
+
+
+def build_pair(core, model_name, model_filters, obs_filters, lc_data, priors, kind="mlp",
+               sample_times=None, error_budget=1.0, systematics=None, detection_limit=np.inf,
+               model_parameters=None):
+    """(GPU likelihood, oracle likelihood, fixed dict, columns)."""
+    from nmma_b200.em import EMTransientLikelihood, FilterSystematicsHandler, SVDLightCurveModel
+    from oracle import harness
+
+    itype = "sklearn_gp" if kind == "gp" else "tensorflow"
+    model = SVDLightCurveModel(model_name, svd_mag_model=core, interpolation_type=itype,
+                               filters=list(model_filters), sample_times=sample_times,
+                               model_parameters=model_parameters)
+    handler = FilterSystematicsHandler(list(obs_filters), systematics, error_budget, lc_data[0])
+    if systematics is not None:
+        handler.setup_systematics_priors(priors)
+    lik = EMTransientLikelihood(model, lc_data, handler, priors, filters=list(obs_filters),
+                                detection_limit=detection_limit)
+    plan = handler.device_plan()
+    olik, fixed = harness.build_oracle_likelihood(
+        oracle_ready_core(core), model.model_parameters, list(model_filters), np.asarray(model.model_times, float),
+        list(obs_filters), lc_data, priors, sys_plan=plan, detection_limit=detection_limit,
+        z_table=model._z_table)
+    return lik, olik, fixed, lik.columns
+
+
+def assert_logl_close(got, ref, rtol=1e-4):
+    """north-star tolerance: |dlogL| <= 1e-4 * max(1, |logL|); sentinel / failure masks bit-exact."""
+    got, ref = np.asarray(got, float), np.asarray(ref, float)
+    sg, sr = got == SENTINEL, ref == SENTINEL
+    assert np.array_equal(sg, sr), f"sentinel masks differ at {np.nonzero(sg != sr)[0][:10]}"
+    ok = ~sr
+    err = np.abs(got[ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))
+    assert err.size == 0 or err.max() <= rtol, f"max rel err {err.max():.3e} (> {rtol})"
+    return float(err.max()) if err.size else 0.0

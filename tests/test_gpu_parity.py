@@ -1,0 +1,410 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances are the north star's: magnitudes within 1e-3 mag, log L within
+1e-4 * max(1, |log L|), failure (sentinel) masks and time indexing bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (GOLDEN, SENTINEL, assert_logl_close, build_pair, fixture_core, oracle_ready_core,
+                     synthetic_observations)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _paths(lik, pts, cols):
+    """logL through every kernel path the configuration supports."""
+    sub = lik.sub_model
+    eng = sub.engine_for(cols)
+    out = {}
+    eng.set_option("path", 2)
+    out["two_stage"] = eng.logl_host(pts)
+    if eng.get_info("fused_supported"):
+        eng.set_option("path", 1)
+        for pt in (1, 2):
+            eng.set_option("points_per_thread", pt)
+            eng.set_option("packed_fma", 0)
+            out[f"fused_pt{pt}"] = eng.logl_host(pts)
+        eng.set_option("packed_fma", 1)
+        out["fused_pt2_packed"] = eng.logl_host(pts)
+        eng.set_option("packed_fma", 0)
+        eng.set_option("points_per_thread", 0)
+    eng.set_option("path", 0)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# C1/C2: Bu2019lm-shaped tensorflow surrogate vs AT2017gfo
+# ------------------------------------------------------------------------------------------------
+def test_bu2019lm_at2017gfo_logl(torch_cuda):
+    from nmma_b200 import synthetic as syn
+    from oracle import harness
+    lc_data, filters = syn.load_at2017gfo(data_tmax=14.0)
+    core = syn.random_model("Bu2019lm", filters, seed=0)
+    priors = syn.bu2019lm_prior()
+    lik, olik, fixed, cols = build_pair(core, "Bu2019lm", filters, filters, lc_data, priors)
+    pts, _ = priors.sample_array(700, np.random.default_rng(1234), cols)
+    ref = harness.oracle_logl(olik, fixed, pts, cols)
+    assert np.isfinite(ref).all() and (ref != SENTINEL).sum() > 600
+    for name, got in _paths(lik, pts, cols).items():
+        err = assert_logl_close(got, ref)
+        print(name, "max rel err", err)
+    # dict entry point == batched entry point
+    p0 = dict(zip(cols, pts[0]))
+    assert lik.log_likelihood(p0) == pytest.approx(ref[0], rel=1e-4)
+
+
+def test_bu2019lm_device_tensor_and_large_batch(torch_cuda):
+    """Size-independent property at a larger N: permuting / tiling the points permutes log L exactly,
+    and every kernel path returns identical values for identical rows."""
+    torch = torch_cuda
+    from nmma_b200 import synthetic as syn
+    lc_data, filters = syn.load_at2017gfo(data_tmax=14.0)
+    core = syn.random_model("Bu2019lm", filters, seed=3)
+    priors = syn.bu2019lm_prior()
+    lik, olik, fixed, cols = build_pair(core, "Bu2019lm", filters, filters, lc_data, priors)
+    base, _ = priors.sample_array(4096, np.random.default_rng(7), cols)
+    reps = 40                                              # 163,840 points: several full waves of tiles
+    pts = np.tile(base, (reps, 1))
+    perm = np.random.default_rng(0).permutation(len(pts))
+    dev = torch.from_numpy(pts[perm]).cuda()
+    out = lik.log_likelihood_batch(dev, cols)
+    assert out.is_cuda and out.dtype == torch.float64
+    out = out.cpu().numpy()
+    unperm = np.empty_like(out)
+    unperm[perm] = out
+    unperm = unperm.reshape(reps, -1)
+    assert np.array_equal(unperm, np.broadcast_to(unperm[0], unperm.shape)), "same row must give the same logL"
+    small = lik.sub_model.engine_for(cols)
+    small.set_option("path", 2)
+    two = small.logl_host(base)
+    small.set_option("path", 0)
+    assert_logl_close(unperm[0], two, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# Fixture weights (real trained surrogate): mags, golden value, logL
+# ------------------------------------------------------------------------------------------------
+def test_fixture_golden_magnitude(torch_cuda):
+    """nmma/tests/joint_analysis_pipeline.py:108-120 through the GPU path: data['ztfr'][10] mag."""
+    from nmma_b200.em import SVDLightCurveModel
+    inj = json.load(open(os.path.join(GOLDEN, "bu2019lm_injection.json")))
+    row = {k: v[0] for k, v in inj.items()}
+    core = fixture_core("mlp", ("ztfr",))
+    sample_times = np.arange(0.1, 10.0 + 0.5, 0.5)
+    model = SVDLightCurveModel("Bu2019nsbh", svd_mag_model=core, interpolation_type="tensorflow",
+                               filters=["ztfr"], sample_times=sample_times)
+    params = model.parameter_conversion(dict(row))
+    tobs, lc = model.gen_detector_lc(params)
+    mask = tobs >= 0
+    mags = lc["ztfr"][mask]
+    noise = np.random.default_rng(42).normal(scale=0.1, size=len(mags))
+    assert len(mags) == 18
+    assert np.isclose((mags + noise)[10], 20.9294036584)
+    assert abs((mags + noise)[10] - 20.9294036584) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["mlp", "gp"])
+def test_fixture_mags_and_logl(torch_cuda, kind):
+    from oracle import harness, nmma_oracle as O
+    from nmma_b200.core.priors import PriorDict, Sine, Uniform
+    from nmma_b200.em import SVDLightCurveModel
+    filters = ["ztfr", "sdssu", "2massks"]
+    core = fixture_core(kind, filters)
+    rng = np.random.default_rng(5)
+    lc_data = synthetic_observations(filters, rng, n_per_filter=12, tmax=15.0, n_ul=2, mag0=19.0)
+    priors = PriorDict()
+    priors["luminosity_distance"] = Uniform(10.0, 200.0)
+    priors["inclination_EM"] = Sine(0.0, np.pi / 2)
+    priors["timeshift"] = Uniform(-0.2, 0.2)
+    priors["log10_mej_dyn"] = Uniform(-2.2, -0.9)      # beyond the training range on purpose: no clipping
+    priors["log10_mej_wind"] = Uniform(-2.2, -0.9)
+    lik, olik, fixed, cols = build_pair(core, "Bu2019nsbh", filters, filters, lc_data, priors, kind=kind)
+    n = 300 if kind == "mlp" else 60
+    pts, _ = priors.sample_array(n, np.random.default_rng(11), cols)
+    ref = harness.oracle_logl(olik, fixed, pts, cols)
+    for name, got in _paths(lik, pts, cols).items():
+        print(kind, name, assert_logl_close(got, ref))
+    # magnitudes: generate_lightcurve / gen_detector_lc vs the oracle, 1e-3 mag
+    model = lik.sub_model.light_curve_model
+    omodel = olik.light_curve_model
+    worst = 0.0
+    for row in pts[:20]:
+        p = dict(fixed)
+        p.update(dict(zip(cols, row)))
+        p = model.parameter_conversion(p)
+        tt = np.asarray(model.model_times, float)
+        mine = model.generate_lightcurve(tt, dict(p))
+        theirs = omodel.generate_lightcurve(tt, dict(p))
+        t_m, app_m = model.gen_detector_lc(dict(p))
+        t_o, app_o = omodel.gen_detector_lc(dict(p))
+        assert np.array_equal(t_m, t_o), "detector-frame time grid must be bit-exact"
+        for f in filters:
+            assert np.array_equal(np.isfinite(mine[f]), np.isfinite(theirs[f]))
+            worst = max(worst, np.abs(mine[f] - theirs[f]).max(), np.abs(app_m[f] - app_o[f]).max())
+    assert worst < 1e-3
+    print(kind, "max |dmag|", worst)
+
+
+def test_mlp_fp32_accuracy_vs_fp64_truth(torch_cuda):
+    """The fp32 summation order differs from NumPy's (and Keras'); both must sit equally close to
+    the exact (fp64) network output."""
+    torch = torch_cuda
+    from nmma_b200.em import SVDLightCurveModel
+    filters = ["ztfr", "sdssu", "2massks"]
+    core = fixture_core("mlp", filters)
+    model = SVDLightCurveModel("Bu2019nsbh", svd_mag_model=core, interpolation_type="tensorflow", filters=filters)
+    eng = model._canonical_engine(np.asarray(model.model_times, float))
+    rng = np.random.default_rng(2)
+    x = rng.uniform([-2.0, -2.0, 0.0], [-1.05, -1.05, 90.0], size=(256, 3))
+    pts = np.concatenate([x, np.full((256, 1), 40.0), np.zeros((256, 2))], axis=1)
+    got = eng.coeffs(pts).cpu().numpy()
+    for fi, f in enumerate(filters):
+        W1, b1, W2, b2 = core[f]["model"]
+        xs = ((x - core[f]["param_mins"]) / (core[f]["param_maxs"] - core[f]["param_mins"])).astype(np.float32)
+        exact = np.maximum(xs.astype(np.float64) @ W1.astype(np.float64) + b1, 0) @ W2.astype(np.float64) + b2
+        npf32 = np.maximum(xs @ W1 + b1, np.float32(0)) @ W2 + b2
+        e_gpu = np.abs(got[:, fi, :] - exact).max()
+        e_np = np.abs(npf32 - exact).max()
+        print(f, "gpu fp32 err", e_gpu, "numpy fp32 err", e_np)
+        assert e_gpu < 2e-5 and e_gpu < 4 * e_np + 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# C3: Bu2023Ye-shaped (d = 7) + time/filter-dependent systematics + upper limits + detection limit
+# ------------------------------------------------------------------------------------------------
+SYS_YAMLS = {
+    "legacy_with_time_all": {"config": {"withTime": {"value": True, "filters": [None], "time_nodes": 4,
+                                                     "type": "Uniform", "minimum": 0, "maximum": 2},
+                                        "withoutTime": {"value": False, "type": "Uniform", "minimum": 0, "maximum": 2}}},
+    "legacy_without_time": {"config": {"withTime": {"value": False, "filters": [None], "time_nodes": 4,
+                                                    "type": "Uniform", "minimum": 0, "maximum": 2},
+                                       "withoutTime": {"value": True, "type": "Uniform", "minimum": 0, "maximum": 2}}},
+    "legacy_groups": {"config": {"withTime": {"value": True, "filters": ["sdssu", ["2massj", "2massh"], "2massks",
+                                                                         ["ps1::g", "ps1::r", "ps1::i", "ps1::z", "ps1::y"]],
+                                              "time_nodes": 3, "type": "Uniform", "minimum": 0.1, "maximum": 2},
+                                 "withoutTime": {"value": False, "type": "Uniform", "minimum": 0, "maximum": 2}}},
+    "new_style_mixed": {"sdssu": {"prior": "Uniform(minimum=0.2, maximum=1.5)"},
+                        "nir": {"filters": ["2massj", "2massh", "2massks"], "time_nodes": 3,
+                                "prior": "Uniform(minimum=0.1, maximum=1.0)"},
+                        "rest": {"time_range": "log 0.5 14 4", "prior": "Uniform(minimum=0.3, maximum=2.0)"}},
+}
+
+
+@pytest.mark.parametrize("sys_name", list(SYS_YAMLS))
+@pytest.mark.parametrize("lim", [np.inf, 24.5])
+def test_bu2023ye_systematics(torch_cuda, sys_name, lim):
+    from nmma_b200 import synthetic as syn
+    from oracle import harness
+    import copy
+    lc_data, filters = syn.load_at2017gfo(data_tmax=14.0)
+    core = syn.random_model("Bu2023Ye", filters, seed=1)
+    priors = syn.bu2023ye_prior()
+    priors["timeshift"].maximum = 0.1
+    lik, olik, fixed, cols = build_pair(core, "Bu2023Ye", filters, filters, lc_data, priors,
+                                        systematics=copy.deepcopy(SYS_YAMLS[sys_name]), detection_limit=lim)
+    assert any(c.startswith("em_syserr") for c in cols)
+    pts, _ = priors.sample_array(200, np.random.default_rng(99), cols)
+    ref = harness.oracle_logl(olik, fixed, pts, cols)
+    for name, got in _paths(lik, pts, cols).items():
+        print(sys_name, lim, name, assert_logl_close(got, ref), "sentinels", int((ref == SENTINEL).sum()))
+
+
+# ------------------------------------------------------------------------------------------------
+# C4: Ka2017-shaped sklearn GP across ZTF + PS1 filters with detection limits
+# ------------------------------------------------------------------------------------------------
+def test_ka2017_gp(torch_cuda):
+    from nmma_b200 import synthetic as syn
+    from oracle import harness
+    filters = ["ztfg", "ztfr", "ztfi", "sdssu", "ps1::g", "ps1::r", "ps1::i", "ps1::z", "ps1::y"]
+    core = syn.random_model("Ka2017", filters, kind="gp", seed=2, Ntr=329)
+    rng = np.random.default_rng(8)
+    lc_data = synthetic_observations(filters, rng, n_per_filter=10, tmax=13.0, n_ul=2, mag0=19.5)
+    limits = {"ztfg": 21.7, "ztfr": 21.4, "ztfi": 20.9, "sdssu": 23.9, "ps1::g": 25.0, "ps1::r": 24.7,
+              "ps1::i": 24.0, "ps1::z": 23.3, "ps1::y": 22.1}
+    priors = syn.ka2017_prior()
+    priors["timeshift"].maximum = 0.2
+    lik, olik, fixed, cols = build_pair(core, "Ka2017", filters, filters, lc_data, priors, kind="gp",
+                                        detection_limit=limits)
+    pts, _ = priors.sample_array(48, np.random.default_rng(21), cols)
+    ref = harness.oracle_logl(olik, fixed, pts, cols)
+    got = lik.log_likelihood_batch(pts, cols)
+    print("ka2017 gp", assert_logl_close(got, ref), "sentinels", int((ref == SENTINEL).sum()))
+    # GP coefficients against sklearn.predict to 1e-9 relative (cancellation ~1e5 in k.alpha)
+    eng = lik.sub_model.engine_for(cols)
+    c_gpu = eng.coeffs(pts[:8]).cpu().numpy()
+    for n in range(8):
+        p = dict(fixed); p.update(dict(zip(cols, pts[n])))
+        x = (np.array([p[k] for k in ["log10_mej", "log10_vej", "log10_Xlan"]]) - core[filters[0]]["param_mins"]) / \
+            (core[filters[0]]["param_maxs"] - core[filters[0]]["param_mins"])
+        for fi, f in enumerate(filters):
+            c_ref = np.array([gp.predict(np.atleast_2d(x))[0] for gp in core[f]["gps"]])
+            scale = np.abs(c_ref).max() + 1e-30
+            assert np.abs(c_gpu[n, fi] - c_ref).max() / scale < 1e-7
+
+
+# ------------------------------------------------------------------------------------------------
+# Two-stage interpolation, averaged filters, edge cases
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("grid", ["tstep", "geom", "partial"])
+def test_two_stage_sample_grid(torch_cuda, grid):
+    """--em-tmin/--em-tmax grids: tt -> sample grid -> observation times."""
+    from oracle import harness
+    from nmma_b200 import synthetic as syn
+    filters = ["ztfr", "sdssu", "2massks"]
+    core = fixture_core("mlp", filters)
+    if grid == "tstep":
+        st = np.arange(0.1, 10.0 + 0.5, 0.5)
+    elif grid == "geom":
+        st = np.geomspace(0.05, 20.0, 150)
+    else:
+        st = np.linspace(-1.0, 25.0, 60)            # nodes outside [0, 21] are dropped in stage 2
+    rng = np.random.default_rng(3)
+    lc_data = synthetic_observations(filters, rng, n_per_filter=9, tmin=0.5, tmax=9.0, n_ul=1, mag0=19.0)
+    from nmma_b200.core.priors import PriorDict, Sine, Uniform
+    priors = PriorDict()
+    priors["luminosity_distance"] = Uniform(20.0, 100.0)
+    priors["inclination_EM"] = Sine(0.0, np.pi / 2)
+    priors["timeshift"] = Uniform(-0.3, 0.3)
+    priors["log10_mej_dyn"] = Uniform(-2.0, -1.05)
+    priors["log10_mej_wind"] = Uniform(-2.0, -1.05)
+    lik, olik, fixed, cols = build_pair(core, "Bu2019nsbh", filters, filters, lc_data, priors, sample_times=st)
+    pts, _ = priors.sample_array(256, np.random.default_rng(4), cols)
+    ref = harness.oracle_logl(olik, fixed, pts, cols)
+    for name, got in _paths(lik, pts, cols).items():
+        print(grid, name, assert_logl_close(got, ref), "sentinels", int((ref == SENTINEL).sum()))
+
+
+def test_out_of_range_detections_and_limits_give_sentinel(torch_cuda):
+    """A detection outside the model's detector-frame window -> truncnorm NaN -> sentinel for the point;
+    an upper limit outside -> logsf = 0; m > detection limit -> -inf -> sentinel."""
+    from oracle import harness
+    from nmma_b200.core.priors import PriorDict, Uniform
+    filters = ["ztfr", "sdssu"]
+    core = fixture_core("mlp", filters)
+    times = {"ztfr": np.array([0.5, 3.0, 20.5, 24.0]), "sdssu": np.array([1.0, 2.0, 30.0])}
+    mags = {"ztfr": np.array([19.0, 20.0, 23.0, 23.0]), "sdssu": np.array([20.0, 21.0, 22.0])}
+    errs = {"ztfr": np.array([0.1, 0.1, 0.2, np.inf]), "sdssu": np.array([0.1, np.inf, np.inf])}
+    lc_data = (times, mags, errs, 0.0)
+    priors = PriorDict()
+    priors["luminosity_distance"] = Uniform(20.0, 60.0)
+    priors["KNtheta"] = Uniform(0.0, 90.0)
+    priors["timeshift"] = Uniform(-1.5, 1.5)          # shifts the 20.5 d detection in and out of range
+    priors["log10_mej_dyn"] = Uniform(-2.0, -1.05)
+    priors["log10_mej_wind"] = Uniform(-2.0, -1.05)
+    for lim in (np.inf, {"ztfr": 19.5, "sdssu": 25.0}):
+        lik, olik, fixed, cols = build_pair(core, "Bu2019nsbh", filters, filters, lc_data, priors, detection_limit=lim)
+        pts, _ = priors.sample_array(300, np.random.default_rng(6), cols)
+        ref = harness.oracle_logl(olik, fixed, pts, cols)
+        nsent = int((ref == SENTINEL).sum())
+        if lim is np.inf:
+            assert 0 < nsent < len(ref)
+        else:
+            assert nsent == len(ref)              # 20.0 > 19.5 limit in ztfr -> -inf for every point
+        for name, got in _paths(lik, pts, cols).items():
+            assert_logl_close(got, ref)
+
+
+def test_averaged_filters(torch_cuda):
+    """Observed filters without a model counterpart are averaged from model filters
+    (nmma/em/utils.py:549-584); only the two-stage kernels serve this configuration."""
+    from oracle import harness, nmma_oracle as O
+    from nmma_b200.core.priors import PriorDict, Uniform
+    # model filters named like the bare bands the averaging rules use
+    src = fixture_core("mlp", ("ztfr", "sdssu", "2massks"))
+    core = {"g": src["sdssu"], "r": src["ztfr"], "i": src["2massks"]}
+    obs_filters = ["g", "r", "i", "w", "o", "V"]
+    rng = np.random.default_rng(12)
+    lc_data = synthetic_observations(obs_filters, rng, n_per_filter=6, tmax=10.0, n_ul=1, mag0=19.0)
+    priors = PriorDict()
+    priors["luminosity_distance"] = Uniform(20.0, 100.0)
+    priors["KNtheta"] = Uniform(0.0, 90.0)
+    priors["log10_mej_dyn"] = Uniform(-2.0, -1.05)
+    priors["log10_mej_wind"] = Uniform(-2.0, -1.05)
+    lik, olik, fixed, cols = build_pair(core, "Bu2019nsbh", ["g", "r", "i"], obs_filters, lc_data, priors)
+    olik.model_filter_mapping, olik.obs_average_mapping = O.get_filter_name_mapping(obs_filters, {"g", "r", "i"})
+    pts, _ = priors.sample_array(128, np.random.default_rng(13), cols)
+    ref = harness.oracle_logl(olik, fixed, pts, cols)
+    eng = lik.sub_model.engine_for(cols)
+    assert eng.get_info("fused_supported") == 0
+    got = lik.log_likelihood_batch(pts, cols)
+    print("averaged", assert_logl_close(got, ref))
+
+
+def test_obs_term_edge_semantics(torch_cuda):
+    """SciPy wrapper semantics of SURVEY.md A.4, evaluated by the device function itself."""
+    from scipy.stats import norm, truncnorm
+    from nmma_b200.engine import KilonovaEngine
+    eng = KilonovaEngine(0)
+    inf, nan = np.inf, np.nan
+    cases = [  # m, mu, sigma_obs, sigma_sys, lim
+        (17.4, 17.5, 0.6, 0.8, inf), (18.0, inf, 0.6, 0.8, inf), (17.4, 17.5, 0.6, 0.8, 22.0),
+        (23.0, 17.5, 0.6, 0.8, 22.0), (19.6, inf, inf, 1.0, inf), (19.6, 18.0, inf, 1.0, inf),
+        (19.6, 0.0, inf, 0.5, inf), (19.6, 45.0, inf, 0.5, inf), (19.0, 18.0, 0.1, 0.0, inf),
+        (19.0, 18.0, inf, 0.0, inf), (19.0, nan, 0.1, 1.0, inf), (19.0, 18.0, nan, 1.0, inf),
+        (19.0, -inf, 0.1, 1.0, inf), (19.0, 18.0, 0.1, 1.0, 18.0), (19.0, 18.0, 0.1, 1.0, 19.0),
+        (19.0, 30.0, 0.1, 1.0, 25.0), (19.0, 18.0, 0.1, -1.0, inf), (19.0, 18.0, inf, -1.0, inf),
+    ]
+    rng = np.random.default_rng(0)
+    for _ in range(400):
+        cases.append((rng.uniform(15, 25), rng.uniform(10, 40), rng.choice([rng.uniform(0.01, 0.5), inf]),
+                      rng.uniform(0.05, 2.0), rng.choice([inf, rng.uniform(18, 26)])))
+    m, mu, so, ss, lim = map(np.array, zip(*cases))
+    got = eng.obs_terms(m, mu, so, ss, lim)
+    ref = np.empty_like(got)
+    with np.errstate(all="ignore"):
+        for i in range(len(got)):
+            sig = np.sqrt(so[i] ** 2 + ss[i] ** 2)
+            if np.isfinite(sig):
+                ref[i] = truncnorm.logpdf(m[i], -np.inf, (lim[i] - mu[i]) / sig, loc=mu[i], scale=sig)
+            else:
+                ref[i] = norm.logsf(m[i], mu[i], ss[i])
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.sign(got[~fin & ~np.isnan(ref)]), np.sign(ref[~fin & ~np.isnan(ref)]))
+    rel = np.abs(got[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))
+    assert rel.max() < 1e-12, rel.max()
+    assert got[6] == pytest.approx(-772.9082649951413, rel=1e-13)
+
+
+def test_nonfinite_inputs_and_empty_batch(torch_cuda):
+    from nmma_b200 import synthetic as syn
+    lc_data, filters = syn.load_at2017gfo(data_tmax=14.0, filters=["ps1::g", "sdssu"])
+    core = syn.random_model("Bu2019lm", filters, seed=0)
+    priors = syn.bu2019lm_prior()
+    lik, olik, fixed, cols = build_pair(core, "Bu2019lm", filters, filters, lc_data, priors)
+    pts, _ = priors.sample_array(16, np.random.default_rng(3), cols)
+    bad = pts.copy()
+    bad[0, cols.index("log10_mej_dyn")] = np.nan
+    bad[1, cols.index("luminosity_distance")] = -5.0
+    bad[2, cols.index("timeshift")] = np.inf
+    bad[3, cols.index("KNphi")] = np.inf
+    for name, got in _paths(lik, bad, cols).items():
+        assert (got[:4] == SENTINEL).all(), name
+        assert (got[4:] != SENTINEL).all(), name
+    assert lik.log_likelihood_batch(np.zeros((0, len(cols))), cols).shape == (0,)
+    one = lik.log_likelihood_batch(pts[:1], cols)
+    assert one.shape == (1,) and one[0] == lik.log_likelihood_batch(pts, cols)[0]
+
+
+def test_abi_error_paths(torch_cuda):
+    from nmma_b200 import _lib as L
+    from nmma_b200.engine import KilonovaEngine
+    eng = KilonovaEngine(0)
+    with pytest.raises(L.NmmaB200Error) as ei:
+        eng.P = 3
+        eng.logl_host(np.zeros((2, 3)))
+    assert ei.value.code == L.ERR_STATE
+    with pytest.raises(L.NmmaB200Error):
+        KilonovaEngine(10 ** 6)
