@@ -628,6 +628,13 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
     return NMMA_B200_OK;
 }
 
+// True when `p` points into page-locked host memory (cudaMallocHost / cudaHostRegister / torch pin_memory).
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host) {
     if (!h) return NMMA_B200_ERR_ARG;
     if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "logl_host: N < 0");
@@ -636,6 +643,8 @@ int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, do
     if (!points_host || !out_host) return fail(h, NMMA_B200_ERR_ARG, "logl_host: NULL pointer");
     CU(cudaSetDevice(h->device));
     const size_t nin = (size_t)N * h->P, nout = (size_t)N;
+    // page-locked caller buffers are copied directly; pageable ones go through pinned staging
+    const bool in_pinned = is_pinned_host(points_host), out_pinned = is_pinned_host(out_host);
     if (nin > h->stage_cap_in) {
         if (h->stage_in_dev) cudaFree(h->stage_in_dev);
         if (h->stage_in_host) cudaFreeHost(h->stage_in_host);
@@ -652,12 +661,14 @@ int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, do
         CU(cudaMallocHost((void**)&h->stage_out_host, nout * sizeof(double)));
         h->stage_cap_out = nout;
     }
-    std::memcpy(h->stage_in_host, points_host, nin * sizeof(double));
-    CU(cudaMemcpyAsync(h->stage_in_dev, h->stage_in_host, nin * sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
+    const double* src = points_host;
+    if (!in_pinned) { std::memcpy(h->stage_in_host, points_host, nin * sizeof(double)); src = h->stage_in_host; }
+    double* dst = out_pinned ? out_host : h->stage_out_host;
+    CU(cudaMemcpyAsync(h->stage_in_dev, src, nin * sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
     if (int rc = nmma_b200_logl(h, h->stage_in_dev, N, h->stage_out_dev, h->own_stream)) return rc;
-    CU(cudaMemcpyAsync(h->stage_out_host, h->stage_out_dev, nout * sizeof(double), cudaMemcpyDeviceToHost, h->own_stream));
+    CU(cudaMemcpyAsync(dst, h->stage_out_dev, nout * sizeof(double), cudaMemcpyDeviceToHost, h->own_stream));
     CU(cudaStreamSynchronize(h->own_stream));
-    std::memcpy(out_host, h->stage_out_host, nout * sizeof(double));
+    if (!out_pinned) std::memcpy(out_host, h->stage_out_host, nout * sizeof(double));
     return NMMA_B200_OK;
 }
 

@@ -143,17 +143,18 @@ class MultiFilterTransient:
         return self._engine
 
     # ---- evaluation -------------------------------------------------------------------------
-    def log_likelihood_batch(self, points, columns: Optional[Sequence[str]] = None):
-        """log L for ``points[N, P]``.  NumPy in -> NumPy out (H2D/D2H inside the C call);
-        CUDA tensor in -> CUDA tensor out (asynchronous on the current stream)."""
+    def log_likelihood_batch(self, points, columns: Optional[Sequence[str]] = None, out=None):
+        """log L for ``points[N, P]``.  NumPy in -> NumPy out (H2D/D2H inside the C call; page-locked
+        arrays are copied without staging); CUDA tensor in -> CUDA tensor out (asynchronous on the
+        current stream).  ``out`` optionally receives the result."""
         eng = self.engine_for(columns)
         is_tensor = hasattr(points, "is_cuda")
         if is_tensor:
-            out = eng.logl_device(points)
+            out = eng.logl_device(points, out=out)
             if self._always_fail:
                 out.fill_(SENTINEL)
             return out
-        out = eng.logl_host(points)
+        out = eng.logl_host(points, out=out)
         if self._always_fail:
             out[:] = SENTINEL
         return out
@@ -204,13 +205,13 @@ class EMTransientLikelihood(NMMALikelihood):
         return self.sub_log_likelihood(parameters)
 
     # ---- batched entry points -------------------------------------------------------------------
-    def log_likelihood_batch(self, points, columns: Optional[Sequence[str]] = None):
+    def log_likelihood_batch(self, points, columns: Optional[Sequence[str]] = None, out=None):
         """``float64[N]`` log L (or sentinel) for ``points[N, P]``; ``columns`` names the P columns
         (default: sampled prior keys in prior order)."""
         if self.constraints:
             raise NotImplementedError("Constraint priors are evaluated per point on the host; "
                                       "use log_likelihood(dict) or drop the constraint for batched sweeps")
-        return self.sub_model.log_likelihood_batch(points, columns)
+        return self.sub_model.log_likelihood_batch(points, columns, out=out)
 
     @property
     def columns(self):

@@ -182,14 +182,17 @@ class KilonovaEngine:
                                                  C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
-    def logl_host(self, points) -> np.ndarray:
-        """log L for host ``points[N,P]`` through ``nmma_b200_logl_host`` (H2D + kernels + D2H)."""
+    def logl_host(self, points, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """log L for host ``points[N,P]`` through ``nmma_b200_logl_host`` (H2D + kernels + D2H).
+        Page-locked arrays (e.g. views of ``torch`` pinned tensors) are copied without staging."""
         pts = _f64(points)
         if pts.ndim == 1:
             pts = pts[None, :]
         if pts.shape[1] != self.P:
             raise ValueError(f"points must have shape [N, {self.P}], got {pts.shape}")
-        out = np.empty(pts.shape[0], np.float64)
+        if out is None:
+            out = np.empty(pts.shape[0], np.float64)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == pts.shape[0]
         self._check(self._lib.nmma_b200_logl_host(self._h, _dptr(pts), pts.shape[0], _dptr(out)))
         return out
 

@@ -63,13 +63,13 @@ def oracle_ready_core(core):
     return out
 
 
-def synthetic_observations(filters, rng, n_per_filter=8, tmin=0.3, tmax=12.0, n_ul=1, mag0=18.0):
+def synthetic_observations(filters, rng, n_per_filter=8, tmin=0.3, tmax=12.0, n_ul=1, mag0=18.0, slope=0.4):
     """(times{f}, mags{f}, errs{f}, trigger) relative to trigger, with `n_ul` upper limits per filter."""
     times, mags, errs = {}, {}, {}
     for f in filters:
         n = int(n_per_filter if np.isscalar(n_per_filter) else n_per_filter[f])
         t = np.sort(rng.uniform(tmin, tmax, n))
-        m = mag0 + 0.4 * t + rng.normal(scale=0.3, size=n)
+        m = mag0 + slope * t + rng.normal(scale=0.3, size=n)
         e = rng.uniform(0.02, 0.3, n)
         idx = rng.choice(n, size=min(n_ul, n), replace=False) if n_ul else []
         for i in idx:

@@ -229,7 +229,7 @@ def test_ka2017_gp(torch_cuda):
     filters = ["ztfg", "ztfr", "ztfi", "sdssu", "ps1::g", "ps1::r", "ps1::i", "ps1::z", "ps1::y"]
     core = syn.random_model("Ka2017", filters, kind="gp", seed=2, Ntr=329)
     rng = np.random.default_rng(8)
-    lc_data = synthetic_observations(filters, rng, n_per_filter=10, tmax=13.0, n_ul=2, mag0=19.5)
+    lc_data = synthetic_observations(filters, rng, n_per_filter=10, tmax=13.0, n_ul=2, mag0=18.0, slope=0.15)
     limits = {"ztfg": 21.7, "ztfr": 21.4, "ztfi": 20.9, "sdssu": 23.9, "ps1::g": 25.0, "ps1::r": 24.7,
               "ps1::i": 24.0, "ps1::z": 23.3, "ps1::y": 22.1}
     priors = syn.ka2017_prior()
