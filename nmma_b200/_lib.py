@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnmma_b200.so")
+LIB_PATH = os.environ.get("NMMA_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnmma_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 XF_NONE, XF_RAD2DEG, XF_LOG10, XF_POW10, XF_THETAJN_DEG, XF_COSTHETAJN_DEG = range(6)

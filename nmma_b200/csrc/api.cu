@@ -66,7 +66,8 @@ struct nmma_b200_handle {
     int opt_path = 0;
     long long opt_fused_min = 2048;
     int opt_max_ctas = 0;
-    int opt_packed = 0;
+    int opt_no_fast = 0;
+    int last_ctas_per_sm = 0;
     int opt_pt = 0;
     long long launches = 0;
     int last_path = 0;
@@ -121,16 +122,16 @@ int check_src(nmma_b200_t* h, const ParamSrc& s, const char* what) {
 
 ParamSrc to_src(const nmma_b200_param_src& s) { return ParamSrc{s.col, s.transform, s.value}; }
 
-template <int D, int PT, bool PACKED>
+template <int D, int PT, bool FAST>
 int launch_fused_dk(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
     constexpr int K = 10;
-    auto kern = fused_mlp_logl_kernel<D, K, PT, PACKED>;
-    const size_t smem = fused_smem_bytes(D, K, h->T);
+    auto kern = fused_mlp_logl_kernel<D, K, PT, FAST>;
+    const size_t smem = fused_smem_bytes(D, K, h->T, h->cfg.S, h->cfg.nobs);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem));
     if (per_sm < 1) return fail(h, NMMA_B200_ERR_CUDA, "fused kernel does not fit on an SM (smem %zu B)", smem);
-    const long long tile = (long long)kFusedConsumers * PT;
+    const long long tile = (long long)kFusedThreads * PT;
     const long long ntiles = (N + tile - 1) / tile;
     long long grid = (long long)h->sm_count * per_sm;
     if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
@@ -138,17 +139,27 @@ int launch_fused_dk(nmma_b200_t* h, const double* pts, long long N, double* out,
     kern<<<(unsigned)grid, kFusedThreads, smem, st>>>(h->cfg, pts, N, out);
     CU(cudaGetLastError());
     h->launches += 1;
+    h->last_ctas_per_sm = per_sm;
     return NMMA_B200_OK;
+}
+
+template <int D, bool FAST>
+int launch_fused_df(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
+    // points per thread: as many as keep every SM busy (a weight fetched from shared memory is
+    // reused PT times; PT = 4 makes the kernel FMA-bound instead of LDS-bound)
+    int pt = h->opt_pt;
+    const long long per_wave = (long long)h->sm_count * kFusedThreads;
+    // measured on B200 (profiles/): PT = 2 at two CTAs per SM beats PT = 4 at one CTA per SM
+    if (pt == 0) pt = (N >= 2 * per_wave) ? 2 : 1;
+    if (pt == 1) return launch_fused_dk<D, 1, FAST>(h, pts, N, out, st);
+    if (pt == 2) return launch_fused_dk<D, 2, FAST>(h, pts, N, out, st);
+    return launch_fused_dk<D, 4, FAST>(h, pts, N, out, st);
 }
 
 template <int D>
 int launch_fused_d(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
-    // points per thread: 2 once there are enough points to keep every SM busy
-    int pt = h->opt_pt;
-    if (pt == 0) pt = (N >= (long long)h->sm_count * kFusedConsumers * 2) ? 2 : 1;
-    if (pt == 1) return launch_fused_dk<D, 1, false>(h, pts, N, out, st);
-    if (h->opt_packed) return launch_fused_dk<D, 2, true>(h, pts, N, out, st);
-    return launch_fused_dk<D, 2, false>(h, pts, N, out, st);
+    const bool fast = h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
+    return fast ? launch_fused_df<D, true>(h, pts, N, out, st) : launch_fused_df<D, false>(h, pts, N, out, st);
 }
 
 int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
@@ -349,13 +360,16 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         for (auto& s : sy_src)
             if (int rc = check_src(h, s, "systematics parameter")) return rc;
         std::vector<int> o_g(nobs);
-        std::vector<double> o_sig(nobs), o_lsc(nobs);
+        std::vector<double> o_sig(nobs), o_lsc(nobs), o_pack((size_t)nobs * kObsRec);
         for (int g = 0; g < G; ++g)
             for (int k = h->g_off[g]; k < h->g_off[g + 1]; ++k) {
                 o_g[k] = g;
                 const double sg = std::sqrt(h->o_s[k] * h->o_s[k] + sy_budget[g] * sy_budget[g]);
                 o_sig[k] = sg;
                 o_lsc[k] = std::log(sg) + NMMA_NORM_PDF_LOGC;
+                double* rec = &o_pack[(size_t)k * kObsRec];
+                rec[0] = h->o_t[k]; rec[1] = h->o_m[k]; rec[2] = h->o_s[k];
+                rec[3] = sg; rec[4] = 1.0 / sg; rec[5] = o_lsc[k];
             }
         std::vector<int> f_goff(F + 1, 0), f_glist;
         bool direct = true;
@@ -375,6 +389,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         if (int rc = upload(h, h->o_s, &c.o_s)) return rc;
         if (int rc = upload(h, o_sig, &c.o_sig)) return rc;
         if (int rc = upload(h, o_lsc, &c.o_lsc)) return rc;
+        if (int rc = upload(h, o_pack, &c.o_pack)) return rc;
         if (int rc = upload(h, sy_mode, &c.sy_mode)) return rc;
         if (int rc = upload(h, sy_budget, &c.sy_budget)) return rc;
         if (int rc = upload(h, sy_nn, &c.sy_nn)) return rc;
@@ -384,7 +399,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         if (int rc = upload(h, f_goff, &c.f_goff)) return rc;
         if (int rc = upload(h, f_glist, &c.f_glist)) return rc;
         h->fused_supported = (h->kind == 0) && direct && fused_has(d, K) &&
-                             fused_smem_bytes(d, K, T) <= 227 * 1024;
+                             fused_smem_bytes(d, K, T, c.S, nobs) <= 227 * 1024;
     }
     h->dirty = false;
     return NMMA_B200_OK;
@@ -716,8 +731,9 @@ int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     if (k == "path") { if (value < 0 || value > 2) return fail(h, NMMA_B200_ERR_ARG, "path must be 0, 1 or 2"); h->opt_path = (int)value; }
     else if (k == "fused_min_points") h->opt_fused_min = value;
     else if (k == "max_ctas") h->opt_max_ctas = (int)value;
-    else if (k == "packed_fma") h->opt_packed = value ? 1 : 0;
-    else if (k == "points_per_thread") { if (value < 0 || value > 2) return fail(h, NMMA_B200_ERR_ARG, "points_per_thread must be 0 (auto), 1 or 2"); h->opt_pt = (int)value; }
+    else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }
+    else if (k == "no_fast_backend") h->opt_no_fast = value ? 1 : 0;
+    else if (k == "points_per_thread") { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, NMMA_B200_ERR_ARG, "points_per_thread must be 0 (auto), 1, 2 or 4"); h->opt_pt = (int)value; }
     else return fail(h, NMMA_B200_ERR_ARG, "unknown option '%s'", key);
     return NMMA_B200_OK;
 }
@@ -728,6 +744,7 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
     if (k == "launches") *value = h->launches;
     else if (k == "last_path") *value = h->last_path;
     else if (k == "sm_count") *value = h->sm_count;
+    else if (k == "ctas_per_sm") *value = h->last_ctas_per_sm;
     else if (k == "fused_supported") { if (int rc = finalize(h, true)) return rc; *value = h->fused_supported ? 1 : 0; }
     else if (k == "algorithmic_flop_per_eval") {
         // F * [2 H (d + K) + 2 T K] (MLP) or Ntr*3d + F*K*Ntr*8 + F*2*T*K (GP)

@@ -55,6 +55,7 @@ struct DevCfg {
     const double* o_s;    // sigma_obs (+inf: upper limit)
     const double* o_sig;  // budget mode: sqrt(sigma_obs^2 + budget^2)
     const double* o_lsc;  // budget mode: log(o_sig) + log(2 pi)/2
+    const double* o_pack; // nobs*6: [t, mag, sigma_obs, o_sig, 1/o_sig, o_lsc] staged into shared memory by the fused kernel
     // systematics per observed filter
     const int* sy_mode;
     const double* sy_budget;

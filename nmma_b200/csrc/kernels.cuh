@@ -271,76 +271,94 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // ---------------------------------------------------------------------------------------------
 // Fused throughput kernel
+//
+// Persistent CTAs of 8 warps; each thread owns PT points (register tiling), so a weight fetched
+// from shared memory as a warp-uniform broadcast is reused PT times.  A broadcast LDS delivers
+// 8 B per wavefront while the FMA pipes consume one 4-byte weight per 2 cycles per SMSP: at
+// PT = 2 the shared-memory pipe and the FMA pipes are exactly balanced (measured 68 % LDS vs 48 %
+// FMA utilisation, profiles/), at PT = 4 the kernel becomes FMA-bound.
+//
+// Per-filter weights stream through a ring of TMA bulk copies (cp.async.bulk -> mbarrier
+// complete_tx).  There is no producer warp: the warp that releases a stage last (shared-memory
+// ticket counter) re-arms its barrier and issues the next bulk copy, so no thread ever spins.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFusedConsumers = 256;              // consumer threads per CTA (8 warps)
-constexpr int kFusedThreads = kFusedConsumers + 32;  // + 1 producer warp
-constexpr int kHC = 256;                          // hidden units per weight chunk
-constexpr int kWStages = 3;                       // weight ring depth
+constexpr int kFusedThreads = 256;   // 8 warps, all consumers
+constexpr int kHC = 128;             // hidden units per weight chunk (8 KB at 16 floats per unit)
+constexpr int kWStages = 6;          // weight ring depth
+constexpr int kObsRec = 6;           // doubles per staged observation record
 
 __host__ __device__ constexpr int fused_rw(int D, int K) { return (D + 1 + K + 3) / 4 * 4; }
-inline size_t fused_smem_bytes(int D, int K, int T) {
+__host__ __device__ inline size_t fused_bslot(int K, int T) {
+    return ((size_t)T * (K + 2) * sizeof(double) + 127) / 128 * 128;
+}
+inline size_t fused_smem_bytes(int D, int K, int T, int S, int nobs) {
     const size_t w = (size_t)kWStages * kHC * fused_rw(D, K) * sizeof(float);
-    size_t b = (size_t)T * (K + 2) * sizeof(double);
-    b = (b + 127) / 128 * 128;
-    return w + 2 * b + 128 /* barriers */;
+    const size_t o = ((size_t)nobs * kObsRec * sizeof(double) + 127) / 128 * 128;
+    const size_t sg = ((size_t)S * sizeof(double) + 127) / 128 * 128;
+    return w + fused_bslot(K, T) + o + sg + 128 /* barriers + tickets */;
 }
 
-template <int D, int K, int PT, bool PACKED>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// FAST = sample grid is the (uniform) training grid itself: stage 1 is the identity and the
+// interval search starts from an O(1) guess.
+template <int D, int K, int PT, bool FAST>
+__global__ void __launch_bounds__(kFusedThreads, (PT >= 4) ? 1 : 2)
 fused_mlp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ out) {
     constexpr int RW = fused_rw(D, K);
-    constexpr int TILE = kFusedConsumers * PT;
+    constexpr int TILE = kFusedThreads * PT;
+    constexpr int NW = kFusedThreads / 32;
+    constexpr uint32_t cbytes = kHC * RW * sizeof(float);
     extern __shared__ __align__(128) unsigned char smem[];  // keeps the shared state space: LDS, not generic LD
     float* wring = reinterpret_cast<float*>(smem);
-    const size_t wbytes = (size_t)kWStages * kHC * RW * sizeof(float);
+    const size_t wbytes = (size_t)kWStages * cbytes;
     const uint32_t bbytes = (uint32_t)(cfg.T * (K + 2) * sizeof(double));
-    const size_t bslot = ((size_t)bbytes + 127) / 128 * 128;
-    double* bring = reinterpret_cast<double*>(smem + wbytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + wbytes + 2 * bslot);
-    uint64_t* full_w = bars;                 // kWStages
-    uint64_t* empty_w = bars + kWStages;     // kWStages
-    uint64_t* full_b = bars + 2 * kWStages;  // 2
-    uint64_t* empty_b = full_b + 2;          // 2
+    const size_t bslot = fused_bslot(K, cfg.T);
+    const size_t obytes = ((size_t)cfg.nobs * kObsRec * sizeof(double) + 127) / 128 * 128;
+    const size_t sbytes = ((size_t)cfg.S * sizeof(double) + 127) / 128 * 128;
+    double* s_basis = reinterpret_cast<double*>(smem + wbytes);
+    double* s_obs = reinterpret_cast<double*>(smem + wbytes + bslot);
+    double* s_samp = reinterpret_cast<double*>(smem + wbytes + bslot + obytes);
+    uint64_t* full_w = reinterpret_cast<uint64_t*>(smem + wbytes + bslot + obytes + sbytes);  // kWStages
+    uint64_t* full_b = full_w + kWStages;                                                     // 1
+    unsigned int* tick_w = reinterpret_cast<unsigned int*>(full_b + 1);                       // kWStages
+    unsigned int* tick_b = tick_w + kWStages;                                                 // 1
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int F = cfg.F;
     const int nch = cfg.HP / kHC;
     const long long ntiles = (N + TILE - 1) / TILE;
+    const long long my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_w = my_tiles * F * nch;  // weight chunks this CTA consumes, in order
+    const long long total_b = my_tiles * F;        // basis packs
+
+    auto issue_w = [&](long long q) {  // chunk q of the sequence: filter (q / nch) % F, chunk q % nch
+        const int st = (int)(q % kWStages);
+        const int f = (int)((q / nch) % F), ch = (int)(q % nch);
+        mbar_arrive_expect_tx(&full_w[st], cbytes);
+        bulk_g2s(wring + (size_t)st * kHC * RW, cfg.wpack + ((size_t)f * cfg.HP + (size_t)ch * kHC) * RW, cbytes,
+                 &full_w[st]);
+    };
+    auto issue_b = [&](long long qb) {
+        const int f = (int)(qb % F);
+        mbar_arrive_expect_tx(full_b, bbytes);
+        bulk_g2s(s_basis, cfg.bpack + (size_t)f * cfg.T * (K + 2), bbytes, full_b);
+    };
 
     if (tid == 0) {
-        for (int i = 0; i < kWStages; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], kFusedConsumers / 32); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], kFusedConsumers / 32); }
+        for (int i = 0; i < kWStages; ++i) { mbar_init(&full_w[i], 1); tick_w[i] = 0; }
+        mbar_init(full_b, 1);
+        tick_b[0] = 0;
         mbar_fence_init();
+        for (long long q = 0; q < kWStages && q < total_w; ++q) issue_w(q);
+        if (total_b > 0) issue_b(0);
     }
+    // observation records + sample grid: staged once per CTA, read as warp-uniform broadcasts
+    for (int i = tid; i < cfg.nobs * kObsRec; i += kFusedThreads) s_obs[i] = cfg.o_pack[i];
+    for (int i = tid; i < cfg.S; i += kFusedThreads) s_samp[i] = cfg.samp[i];
     __syncthreads();
 
-    if (warp == kFusedConsumers / 32) {
-        // ---------------- producer warp: stream basis packs and weight chunks ----------------
-        if (lane == 0) {
-            uint32_t ws = 0, wph = 0, bs = 0, bph = 0;
-            constexpr uint32_t cbytes = kHC * RW * sizeof(float);
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int f = 0; f < F; ++f) {
-                    mbar_wait(&empty_b[bs], bph ^ 1);
-                    mbar_arrive_expect_tx(&full_b[bs], bbytes);
-                    bulk_g2s(reinterpret_cast<unsigned char*>(bring) + bs * bslot,
-                             cfg.bpack + (size_t)f * cfg.T * (K + 2), bbytes, &full_b[bs]);
-                    if (++bs == 2) { bs = 0; bph ^= 1; }
-                    const float* wsrc = cfg.wpack + (size_t)f * cfg.HP * RW;
-                    for (int ch = 0; ch < nch; ++ch) {
-                        mbar_wait(&empty_w[ws], wph ^ 1);
-                        mbar_arrive_expect_tx(&full_w[ws], cbytes);
-                        bulk_g2s(wring + (size_t)ws * kHC * RW, wsrc + (size_t)ch * kHC * RW, cbytes, &full_w[ws]);
-                        if (++ws == kWStages) { ws = 0; wph ^= 1; }
-                    }
-                }
-            }
-        }
-        return;
-    }
-
-    // -------------------------------- consumer warps ---------------------------------------
-    uint32_t ws = 0, wph = 0, bs = 0, bph = 0;
+    long long q = 0, qb = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         long long n[PT];
         bool live[PT];
@@ -349,7 +367,7 @@ fused_mlp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long lon
         bool ok[PT];
 #pragma unroll
         for (int p = 0; p < PT; ++p) {
-            n[p] = tile * TILE + (long long)p * kFusedConsumers + tid;  // coalesced across the warp
+            n[p] = tile * TILE + (long long)p * kFusedThreads + tid;  // coalesced across the warp
             live[p] = n[p] < N;
             const double* row = pts + (live[p] ? n[p] : 0) * cfg.P;
             ps[p] = point_setup(cfg, row);
@@ -369,42 +387,46 @@ fused_mlp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long lon
                     x[p][i] = (float)xs;
                 }
             }
-            // ---- MLP: fp32 FFMA, two-level accumulation (per chunk, then total) ----
+            // ---- MLP: fp32 FMA, two-level accumulation (per 4 chunks, then total) ----
             float ctot[PT][K];
 #pragma unroll
             for (int p = 0; p < PT; ++p)
 #pragma unroll
                 for (int k = 0; k < K; ++k) ctot[p][k] = 0.f;
-            for (int ch = 0; ch < nch; ++ch) {
-                mbar_wait(&full_w[ws], wph);
-                const float4* wq = reinterpret_cast<const float4*>(wring + (size_t)ws * kHC * RW);
-                float acc[PT][K];
+            float acc[PT][K];
 #pragma unroll
-                for (int p = 0; p < PT; ++p)
+            for (int p = 0; p < PT; ++p)
 #pragma unroll
-                    for (int k = 0; k < K; ++k) acc[p][k] = 0.f;
-#pragma unroll 4
+                for (int k = 0; k < K; ++k) acc[p][k] = 0.f;
+            for (int ch = 0; ch < nch; ++ch, ++q) {
+                const int st = (int)(q % kWStages);
+                mbar_wait(&full_w[st], (uint32_t)((q / kWStages) & 1));
+                const float4* wq = reinterpret_cast<const float4*>(wring + (size_t)st * kHC * RW);
+#pragma unroll 2
                 for (int j = 0; j < kHC; ++j) {
                     float w[RW];
 #pragma unroll
-                    for (int q = 0; q < RW / 4; ++q) {
-                        const float4 v = wq[j * (RW / 4) + q];  // warp-uniform address: LDS.128 broadcast
-                        w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                    for (int qq = 0; qq < RW / 4; ++qq) {
+                        const float4 v = wq[j * (RW / 4) + qq];  // warp-uniform address: LDS.128 broadcast
+                        w[4 * qq + 0] = v.x; w[4 * qq + 1] = v.y; w[4 * qq + 2] = v.z; w[4 * qq + 3] = v.w;
                     }
-                    if constexpr (PACKED && PT == 2) {
-                        // two points share one packed fma.rn.f32x2 (sm_100 FFMA2)
-                        float2 h = make_float2(w[D], w[D]);
+                    if constexpr (PT % 2 == 0) {
+                        // point pairs share one packed fma.rn.f32x2 (sm_100 FFMA2, scalar weight broadcast)
 #pragma unroll
-                        for (int i = 0; i < D; ++i)
-                            h = __ffma2_rn(make_float2(x[0][i], x[1][i]), make_float2(w[i], w[i]), h);
-                        h.x = fmaxf(h.x, 0.f);
-                        h.y = fmaxf(h.y, 0.f);
+                        for (int pp = 0; pp < PT; pp += 2) {
+                            float2 h = make_float2(w[D], w[D]);
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const float2 r = __ffma2_rn(h, make_float2(w[D + 1 + k], w[D + 1 + k]),
-                                                        make_float2(acc[0][k], acc[1][k]));
-                            acc[0][k] = r.x;
-                            acc[1][k] = r.y;
+                            for (int i = 0; i < D; ++i)
+                                h = __ffma2_rn(make_float2(x[pp][i], x[pp + 1][i]), make_float2(w[i], w[i]), h);
+                            h.x = fmaxf(h.x, 0.f);
+                            h.y = fmaxf(h.y, 0.f);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const float2 r = __ffma2_rn(h, make_float2(w[D + 1 + k], w[D + 1 + k]),
+                                                            make_float2(acc[pp][k], acc[pp + 1][k]));
+                                acc[pp][k] = r.x;
+                                acc[pp + 1][k] = r.y;
+                            }
                         }
                     } else {
 #pragma unroll
@@ -418,54 +440,119 @@ fused_mlp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long lon
                         }
                     }
                 }
+                // release the stage; the last warp to arrive refills it with chunk q + kWStages
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_w[ws]);
-                if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                if (lane == 0) {
+                    const unsigned int old = atomicAdd(&tick_w[st], 1u);
+                    if ((old % NW) == NW - 1 && q + kWStages < total_w) {
+                        fence_proxy_async();
+                        issue_w(q + kWStages);
+                    }
+                }
+                if ((ch & 3) == 3 || ch == nch - 1) {
 #pragma unroll
-                for (int p = 0; p < PT; ++p)
+                    for (int p = 0; p < PT; ++p)
 #pragma unroll
-                    for (int k = 0; k < K; ++k) ctot[p][k] += acc[p][k];
+                        for (int k = 0; k < K; ++k) { ctot[p][k] += acc[p][k]; acc[p][k] = 0.f; }
+                }
             }
-            // ---- coefficients: + b2 in fp32 (Keras Dense), then fp64 for the rest ----
-            double c[PT][K];
+            // ---- back end for the observed filters that map onto f ----
+            mbar_wait(full_b, (uint32_t)(qb & 1));
+            const double* bp = s_basis;
+            const int lo = cfg.s_lo[f], hi = cfg.s_hi[f];
 #pragma unroll
-            for (int p = 0; p < PT; ++p)
+            for (int p = 0; p < PT; ++p) {
+                // coefficients: + b2 in fp32 (Keras Dense), then fp64 for the rest
+                double cp[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const float cf = ctot[p][k] + cfg.b2[f * K + k];
                     ok[p] = ok[p] && isfinite(cf);
-                    c[p][k] = (double)cf;
+                    cp[k] = (double)cf;
                 }
-            // ---- back end for the observed filters that map onto f ----
-            mbar_wait(&full_b[bs], bph);
-            const double* bp = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(bring) + bs * bslot);
-            for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
-                const int g = cfg.f_glist[gi];
-                const double lim = cfg.g_lim[g];
-                const int mode = cfg.sy_mode[g];
-                for (int k = cfg.g_off[g]; k < cfg.g_off[g + 1]; ++k) {
-                    const double t = cfg.o_t[k], m = cfg.o_m[k], so = cfg.o_s[k];
-#pragma unroll
-                    for (int p = 0; p < PT; ++p) {
-                        if (!ok[p]) continue;
-                        const double* cp = c[p];
-                        auto node = [&](int j) { return node_mag_k<K>(bp, j, cp); };
-                        auto abs_at = [&](int s) { return sample_mag(cfg, f, s, node); };
-                        const double mu = interp_obs(cfg, f, t, ps[p], abs_at);
+                if (!ok[p]) continue;
+                const double z1 = ps[p].z1, tsh = ps[p].ts;
+                const double inv_z1 = 1.0 / z1;
+                const double tlo = __dadd_rn(__dmul_rn(s_samp[lo], z1), tsh);
+                const double thi = __dadd_rn(__dmul_rn(s_samp[hi], z1), tsh);
+                double lsum = 0.0;
+                for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
+                    const int g = cfg.f_glist[gi];
+                    const double lim = cfg.g_lim[g];
+                    const int mode = cfg.sy_mode[g];
+                    const int k1 = cfg.g_off[g + 1];
+                    for (int k = cfg.g_off[g]; k < k1; ++k) {
+                        const double* rec = s_obs + k * kObsRec;  // t, mag, sigma_obs, sigma, 1/sigma, log(sigma)+C
+                        const double t = rec[0], m = rec[1], so = rec[2];
+                        double mu;
+                        if constexpr (FAST) {
+                            if (t < tlo || t > thi) {
+                                mu = CUDART_INF;  // np.interp left = right = +inf
+                            } else {
+                                // interval search: O(1) guess from the inverse map, settled by the exact
+                                // (mul, add) comparisons np.interp's bisection would make
+                                const double gq = (__dsub_rn(t, tsh) * inv_z1 - cfg.uni_s0) * cfg.uni_inv_ds;
+                                int j = (gq >= (double)hi) ? hi : ((gq <= (double)lo) ? lo : (int)gq);
+                                double tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh);
+                                double tj1 = (j < hi) ? __dadd_rn(__dmul_rn(s_samp[j + 1], z1), tsh) : CUDART_INF;
+                                int guard = 0;
+                                while (tj > t && j > lo && guard < 8) {
+                                    --j; tj1 = tj; tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh); ++guard;
+                                }
+                                while (j < hi && tj1 <= t && guard < 8) {
+                                    ++j; tj = tj1;
+                                    tj1 = (j < hi) ? __dadd_rn(__dmul_rn(s_samp[j + 1], z1), tsh) : CUDART_INF;
+                                    ++guard;
+                                }
+                                if (!(tj <= t && (j == hi || tj1 > t))) {  // cold: fall back to bisection
+                                    j = locate(cfg, lo, hi, t, z1, tsh);
+                                    tj = tobs_at(cfg, j, z1, tsh);
+                                    tj1 = (j < hi) ? tobs_at(cfg, j + 1, z1, tsh) : CUDART_INF;
+                                }
+                                const double a0 = __dadd_rn(__dadd_rn(node_mag_k<K>(bp, j, cp), ps[p].dm), ps[p].zc);
+                                if (j == hi || tj == t) {
+                                    mu = a0;
+                                } else {
+                                    const double a1 = __dadd_rn(__dadd_rn(node_mag_k<K>(bp, j + 1, cp), ps[p].dm), ps[p].zc);
+                                    // slope * (t - tj) + a0 with the interpolation weight in fp32: the weight only
+                                    // scales (a1 - a0) <~ 1 mag, so its 6e-8 relative error is < 1e-7 mag
+                                    const float wgt = __fdividef((float)__dsub_rn(t, tj), (float)__dsub_rn(tj1, tj));
+                                    mu = fma(__dsub_rn(a1, a0), (double)wgt, a0);
+                                    if (isnan(mu) && a0 == a1) mu = a0;
+                                }
+                            }
+                        } else {
+                            auto node = [&](int j) { return node_mag_k<K>(bp, j, cp); };
+                            auto abs_at = [&](int s) { return sample_mag(cfg, f, s, node); };
+                            mu = interp_obs(cfg, f, t, ps[p], abs_at);
+                        }
                         double term;
-                        if (mode == 0 && isfinite(so)) {
-                            term = obs_term_static_det(m, mu, cfg.o_sig[k], cfg.o_lsc[k], lim);
+                        if (FAST && mode == 0 && lim == CUDART_INF && isfinite(so)) {
+                            // truncnorm.logpdf with b = +inf: NaN when mu is +inf/NaN (b = inf - inf), else the
+                            // plain Gaussian log-density with the staged 1/sigma and log(sigma) + log(2 pi)/2
+                            const double xq = __dsub_rn(m, mu) * rec[4];
+                            term = (mu < CUDART_INF) ? (-0.5 * (xq * xq) - rec[5]) : CUDART_NAN;
+                        } else if (mode == 0 && isfinite(so)) {
+                            term = obs_term_static_det(m, mu, rec[3], rec[5], lim);
                         } else {
                             const double* row = pts + (live[p] ? n[p] : 0) * cfg.P;
                             term = obs_term(m, mu, so, sys_sigma(cfg, g, t, row), lim);
                         }
-                        logl[p] += term;
+                        lsum += term;
                     }
                 }
+                logl[p] += lsum;
             }
+            // release the basis pack; the last warp to arrive loads the next filter's pack
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_b[bs]);
-            if (++bs == 2) { bs = 0; bph ^= 1; }
+            if (lane == 0) {
+                const unsigned int old = atomicAdd(tick_b, 1u);
+                if ((old % NW) == NW - 1 && qb + 1 < total_b) {
+                    fence_proxy_async();
+                    issue_b(qb + 1);
+                }
+            }
+            ++qb;
         }
 #pragma unroll
         for (int p = 0; p < PT; ++p)

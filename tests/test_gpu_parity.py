@@ -31,13 +31,12 @@ def _paths(lik, pts, cols):
     out["two_stage"] = eng.logl_host(pts)
     if eng.get_info("fused_supported"):
         eng.set_option("path", 1)
-        for pt in (1, 2):
+        for pt in (1, 2, 4):
             eng.set_option("points_per_thread", pt)
-            eng.set_option("packed_fma", 0)
             out[f"fused_pt{pt}"] = eng.logl_host(pts)
-        eng.set_option("packed_fma", 1)
-        out["fused_pt2_packed"] = eng.logl_host(pts)
-        eng.set_option("packed_fma", 0)
+            eng.set_option("no_fast_backend", 1)          # generic back end (two np.interp stages)
+            out[f"fused_pt{pt}_generic"] = eng.logl_host(pts)
+            eng.set_option("no_fast_backend", 0)
         eng.set_option("points_per_thread", 0)
     eng.set_option("path", 0)
     return out
