@@ -14,7 +14,7 @@ def distance_modulus_nmma(d_lum=1e-5):
 def get_cosmo_grids(distance_min, distance_max, cosmology=None):
     """``nmma/core/conversion.py:49-55``: 50-point geometric redshift grid between the prior bounds."""
     cosmology = cosmology or get_cosmology()
-    zmin = cosmology.z_at_luminosity_distance(distance_min)
+    zmin = cosmology.z_at_luminosity_distance(distance_min) if distance_min > 0 else 0.0
     zmax = cosmology.z_at_luminosity_distance(distance_max)
     if not (zmin > 0):
         # the reference calls np.geomspace(0, ...) here (priors with luminosity_distance minimum 0.0)

@@ -82,33 +82,32 @@ class MultiFilterTransient:
             raise KeyError(name)
         return model._eval_filters.index(name)
 
-    def _build_engine(self, columns: Sequence[str]):
+    def plan_layout(self, columns: Sequence[str]) -> dict:
+        """Host-only: everything the engine needs for ``columns`` (no device access)."""
         model = self.light_curve_model
-        eng = model.new_engine()
-        eng.set_sample_grid(np.asarray(model.model_times, float))
         avail = self._available(columns)
-        xsrc = resolve_param_sources(model.model_parameters, avail)
-        dl = avail.get("luminosity_distance", ParamSrc.const(1e-5))
-        ts = avail.get("timeshift", ParamSrc.const(0.0))
+        plan = dict(P=len(columns))
+        plan["xsrc"] = resolve_param_sources(model.model_parameters, avail)
+        plan["dl"] = avail.get("luminosity_distance", ParamSrc.const(1e-5))
+        plan["ts"] = avail.get("timeshift", ParamSrc.const(0.0))
         if "Ebv" in avail and not (avail["Ebv"].col < 0 and avail["Ebv"].value == 0.0):
             raise NotImplementedError("extinction (Ebv != 0) is not part of this build (DESIGN.md, 'next' rows)")
+        plan["z_table"] = None
         if "redshift" in avail:
-            zsrc, zmode = avail["redshift"], L.Z_PARAM
+            plan["zsrc"], plan["zmode"] = avail["redshift"], L.Z_PARAM
         elif "luminosity_distance" in avail:
             if model._z_table is None:
                 raise ValueError("luminosity_distance is sampled but not in the priors: the per-call "
                                  "z_at_value path of the reference is not available in batched mode")
-            eng.set_redshift_table(*model._z_table)
-            zsrc, zmode = ParamSrc.const(0.0), L.Z_TABLE
+            plan["z_table"] = model._z_table
+            plan["zsrc"], plan["zmode"] = ParamSrc.const(0.0), L.Z_TABLE
         else:
-            zsrc, zmode = ParamSrc.const(0.0), L.Z_ZERO
-        eng.set_param_layout(len(columns), xsrc, dl, ts, zsrc, zmode)
-
+            plan["zsrc"], plan["zmode"] = ParamSrc.const(0.0), L.Z_ZERO
         # a model filter the surrogate cannot evaluate is all-inf -> sanity_check fails for every point
-        self._always_fail = any(f not in model._eval_filters for f in model.filters)
+        plan["always_fail"] = any(f not in model._eval_filters for f in model.filters)
 
-        plan = self.systematics_handler.device_plan()
-        obs_filters = [f for f in plan.keys()]          # band_log_likelihood iterates obs_error.items()
+        sysplan = self.systematics_handler.device_plan()
+        obs_filters = [f for f in sysplan.keys()]          # band_log_likelihood iterates obs_error.items()
         helper_lists, times, mags, sigmas, limits = [], [], [], [], []
         modes, budgets, node_srcs, node_times = [], [], [], []
         for filt in obs_filters:
@@ -121,7 +120,7 @@ class MultiFilterTransient:
             mags.append(np.asarray(self.light_curves[filt], float))
             sigmas.append(np.asarray(self.light_curve_uncertainties[filt], float))
             limits.append(float(self.detection_limit[filt]))
-            entry = plan[filt]
+            entry = sysplan[filt]
             if entry[0] == "budget":
                 modes.append(L.SYS_BUDGET); budgets.append(entry[1]); node_srcs.append([]); node_times.append([])
             elif entry[0] == "param":
@@ -130,8 +129,22 @@ class MultiFilterTransient:
             else:
                 modes.append(L.SYS_INTERP); budgets.append(0.0)
                 node_srcs.append([avail[n] for n in entry[1]]); node_times.append(list(entry[2]))
-        eng.set_observations(helper_lists, times, mags, sigmas, limits)
-        eng.set_systematics(modes, budgets, node_srcs, node_times)
+        plan["obs"] = (helper_lists, times, mags, sigmas, limits)
+        plan["sys"] = (modes, budgets, node_srcs, node_times)
+        plan["obs_filters"] = obs_filters
+        return plan
+
+    def _build_engine(self, columns: Sequence[str]):
+        model = self.light_curve_model
+        plan = self.plan_layout(columns)
+        eng = model.new_engine()
+        eng.set_sample_grid(np.asarray(model.model_times, float))
+        if plan["z_table"] is not None:
+            eng.set_redshift_table(*plan["z_table"])
+        eng.set_param_layout(plan["P"], plan["xsrc"], plan["dl"], plan["ts"], plan["zsrc"], plan["zmode"])
+        eng.set_observations(*plan["obs"])
+        eng.set_systematics(*plan["sys"])
+        self._always_fail = plan["always_fail"]
         self._engine = eng
         self._columns = list(columns)
         return eng
