@@ -59,10 +59,13 @@ class ShardedEvaluator:
         if len(set(sizes)) == 1:
             out = torch.empty(n_global, dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(out, t, group=self.group)   # ncclAllGather over NVLink
-        else:
-            parts = [torch.empty(s, dtype=t.dtype, device=t.device) for s in sizes]
-            dist.all_gather(parts, t, group=self.group)
-            out = torch.cat(parts)
+        else:   # ragged tail: pad every block to the largest one, gather, trim
+            m = max(sizes)
+            padded = torch.zeros(m, dtype=t.dtype, device=t.device)
+            padded[:t.numel()] = t
+            buf = torch.empty(m * self.world, dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(buf, padded, group=self.group)
+            out = torch.cat([buf[r * m:r * m + sizes[r]] for r in range(self.world)])
         if dst is not None and self.rank != dst:
             return None
         return out
