@@ -111,3 +111,62 @@ def assert_logl_close(got, ref, rtol=1e-4):
     err = np.abs(got[ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))
     assert err.size == 0 or err.max() <= rtol, f"max rel err {err.max():.3e} (> {rtol})"
     return float(err.max()) if err.size else 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# Golden vectors produced by the reference's own source files (tests/golden/make_reference_vectors.py)
+# ---------------------------------------------------------------------------------------------
+_YAML_WITH_TIME = {"config": {"withTime": {"value": True, "filters": [None], "time_nodes": 4, "type": "Uniform",
+                                            "minimum": 0, "maximum": 2},
+                              "withoutTime": {"value": False, "type": "Uniform", "minimum": 0, "maximum": 2}}}
+_YAML_WITHOUT_TIME = {"config": {"withTime": {"value": False, "filters": [None], "time_nodes": 4, "type": "Uniform",
+                                               "minimum": 0, "maximum": 2},
+                                 "withoutTime": {"value": True, "type": "Uniform", "minimum": 0, "maximum": 2}}}
+REFERENCE_CASES = {
+    "A": dict(kind="mlp", filters=["ztfr", "sdssu", "2massks"], sample_times=None, budget=1.0, yaml=None, limit=np.inf),
+    "B": dict(kind="mlp", filters=["ztfr", "sdssu", "2massks"], sample_times=np.arange(0.1, 10.0 + 0.5, 0.5),
+              budget=0.5, yaml=None, limit=np.inf),
+    "C": dict(kind="mlp", filters=["ztfr", "sdssu", "2massks"], sample_times=None, budget=1.0, yaml=_YAML_WITH_TIME,
+              limit={"ztfr": 23.5, "sdssu": 24.0, "2massks": 23.0}),
+    "D": dict(kind="gp", filters=["ztfr"], sample_times=None, budget=0.8, yaml=None, limit=np.inf),
+    "E": dict(kind="mlp", filters=["ztfr", "sdssu", "2massks"], sample_times=None, budget=1.0, yaml=_YAML_WITHOUT_TIME,
+              limit=np.inf),
+}
+
+
+def reference_case(name):
+    """Rebuild case `name` of make_reference_vectors.py: (cfg, lc_data, priors, golden dict)."""
+    import copy
+    from nmma_b200.core.priors import PriorDict, Sine, Uniform
+    z = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+    cfg = copy.deepcopy(REFERENCE_CASES[name])
+    times, mags, errs = {}, {}, {}
+    for f in cfg["filters"]:
+        key = f.replace(":", "_")
+        times[f], mags[f], errs[f] = (z[f"{name}/obs/{key}/{k}"] for k in ("time", "mag", "mag_error"))
+    priors = PriorDict()
+    priors["luminosity_distance"] = Uniform(10.0, 200.0, name="luminosity_distance")
+    priors["inclination_EM"] = Sine(0.0, np.pi / 2, name="inclination_EM")
+    priors["timeshift"] = Uniform(-0.3, 0.3, name="timeshift")
+    priors["log10_mej_dyn"] = Uniform(-2.2, -0.9, name="log10_mej_dyn")
+    priors["log10_mej_wind"] = Uniform(-2.2, -0.9, name="log10_mej_wind")
+    gold = {k: z[f"{name}/{k}"] for k in ("points", "columns", "logl", "mags", "tobs", "z_table")}
+    gold["columns"] = [str(c) for c in gold["columns"]]
+    return cfg, (times, mags, errs, 57000.0), priors, gold
+
+
+def build_reference_pair(name):
+    """(GPU likelihood, oracle likelihood, fixed, cols, golden) for a reference-generated case."""
+    cfg, lc_data, priors, gold = reference_case(name)
+    core = fixture_core(cfg["kind"], tuple(cfg["filters"]))
+    lik, olik, fixed, cols = build_pair(core, "Bu2019nsbh", cfg["filters"], cfg["filters"], lc_data, priors,
+                                        kind=cfg["kind"], sample_times=cfg["sample_times"], error_budget=cfg["budget"],
+                                        systematics=cfg["yaml"], detection_limit=cfg["limit"])
+    assert cols == gold["columns"], (cols, gold["columns"])
+    # evaluate with the very dL -> z table the reference run used
+    table = (gold["z_table"][0], gold["z_table"][1])
+    lik.sub_model.light_curve_model._z_table = table
+    lik.sub_model.light_curve_model.redshift_func = lambda p: np.interp(p["luminosity_distance"], *table)
+    lik.sub_model._engine = None
+    olik.light_curve_model.check_vs_priors(table=table)
+    return lik, olik, fixed, cols, gold
