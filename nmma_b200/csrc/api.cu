@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "kernels.cuh"
+#include "tc_kernel.cuh"
 
 using namespace nmma;
 
@@ -54,6 +54,7 @@ struct nmma_b200_handle {
     std::vector<void*> dev_allocs;
     DevCfg cfg{};
     bool fused_supported = false;
+    bool tc_supported = false;
     double* coeff_scratch = nullptr;
     size_t coeff_cap = 0;
     double* stage_in_dev = nullptr;
@@ -65,6 +66,7 @@ struct nmma_b200_handle {
     // ---- knobs / counters ----
     int opt_path = 0;
     long long opt_fused_min = 2048;
+    long long opt_tc_min = 1LL << 62;  // tensor-core path: opt-in until measured faster (set_option "tc_min_points")
     int opt_max_ctas = 0;
     int opt_no_fast = 0;
     int last_ctas_per_sm = 0;
@@ -175,6 +177,38 @@ int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cu
 }
 
 bool fused_has(int d, int K) { return d >= 2 && d <= 7 && K == 10; }
+
+template <bool FAST>
+int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
+    constexpr int K = 10;
+    auto kern = fused_tc_logl_kernel<K, FAST>;
+    const size_t smem = tc_smem_bytes(K, h->T, h->cfg.S, h->cfg.nobs);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long super = (long long)kTcTile * kTcTiles;
+    const long long nsuper = (N + super - 1) / super;
+    long long grid = h->sm_count;  // one CTA per SM: each CTA owns all 512 TMEM columns of its SM
+    if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
+    grid = std::max<long long>(1, std::min(grid, nsuper));
+    kern<<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, out);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->last_ctas_per_sm = 1;
+    return NMMA_B200_OK;
+}
+
+int launch_tc(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
+    const bool fast = h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
+    return fast ? launch_tc_f<true>(h, pts, N, out, st) : launch_tc_f<false>(h, pts, N, out, st);
+}
+
+// hi = the 19 bits kind::tf32 reads, lo = remainder (exact in fp32; the tensor core truncates it again)
+inline void tf32_split(float w, float* hi, float* lo) {
+    uint32_t u;
+    std::memcpy(&u, &w, 4);
+    u &= 0xFFFFE000u;
+    std::memcpy(hi, &u, 4);
+    *lo = std::isfinite(w) ? (w - *hi) : 0.f;
+}
 
 int ensure_scratch(nmma_b200_t* h, size_t n_doubles) {
     if (n_doubles <= h->coeff_cap) return NMMA_B200_OK;
@@ -317,6 +351,31 @@ int finalize(nmma_b200_t* h, bool need_obs) {
             }
         if (int rc = upload(h, wpack, &c.wpack)) return rc;
         if (int rc = upload(h, h->b2, &c.b2)) return rc;
+        // tensor-core operand tiles (tc_kernel.cuh): K-major, no swizzle, hi/lo split
+        c.tc_nch = 0;
+        c.tcpack = nullptr;
+        if (d + 1 <= 8 && K <= kTcN2) {
+            int nch = (H + kTcChunk - 1) / kTcChunk;
+            nch += nch & 1;
+            c.tc_nch = nch;
+            std::vector<float> tp((size_t)F * nch * kTcChunkFloats, 0.f);
+            for (int f = 0; f < F; ++f)
+                for (int j = 0; j < H; ++j) {
+                    float* ch = &tp[((size_t)f * nch + j / kTcChunk) * kTcChunkFloats];
+                    const int n = j % kTcChunk;
+                    for (int k = 0; k <= d; ++k) {
+                        const float w = (k < d) ? h->W1[((size_t)f * d + k) * H + j] : h->b1[(size_t)f * H + j];
+                        tf32_split(w, &ch[tc_b_index(kTcChunk, n, k)], &ch[256 + tc_b_index(kTcChunk, n, k)]);
+                    }
+                    const int s = n / 8, kk = n % 8;
+                    for (int o = 0; o < K; ++o) {
+                        const float w = h->W2[((size_t)f * H + j) * K + o];
+                        tf32_split(w, &ch[512 + s * 128 + tc_b_index(kTcN2, o, kk)],
+                                   &ch[1024 + s * 128 + tc_b_index(kTcN2, o, kk)]);
+                    }
+                }
+            if (int rc = upload(h, tp, &c.tcpack)) return rc;
+        }
     } else {
         c.Ntr = h->Ntr;
         // GP inputs are scaled with filter 0's param_mins/maxs: training shares them (em/training.py:216-230)
@@ -340,6 +399,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
 
     // ---- observations + systematics ----
     h->fused_supported = false;
+    h->tc_supported = false;
     if (h->have_obs) {
         const int G = h->G;
         const int nobs = h->g_off[G];
@@ -400,6 +460,8 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         if (int rc = upload(h, f_glist, &c.f_glist)) return rc;
         h->fused_supported = (h->kind == 0) && direct && fused_has(d, K) &&
                              fused_smem_bytes(d, K, T, c.S, nobs) <= 227 * 1024;
+        h->tc_supported = (h->kind == 0) && direct && K == 10 && c.tc_nch > 0 &&
+                          tc_smem_bytes(K, T, c.S, nobs) <= 227 * 1024;
     }
     h->dirty = false;
     return NMMA_B200_OK;
@@ -624,8 +686,14 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
     int path = h->opt_path;
     if (path == 1 && !h->fused_supported)
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused kernel unavailable for this configuration (GP path, averaged filters, or d/K not instantiated)");
-    if (path == 0) path = (h->fused_supported && N >= h->opt_fused_min) ? 1 : 2;
+    if (path == 3 && !h->tc_supported)
+        return fail(h, NMMA_B200_ERR_UNSUPPORTED, "tensor-core kernel unavailable for this configuration (GP path, averaged filters, d > 7 or n_coeff != 10)");
+    if (path == 0) {
+        if (h->tc_supported && N >= h->opt_tc_min) path = 3;
+        else path = (h->fused_supported && N >= h->opt_fused_min) ? 1 : 2;
+    }
     h->last_path = path;
+    if (path == 3) return launch_tc(h, points_dev, N, out_dev, st);
     if (path == 1) return launch_fused(h, points_dev, N, out_dev, st);
     const size_t FK = (size_t)h->F * h->K;
     const long long chunk = std::min<long long>(N, kTwoStageChunk);
@@ -728,8 +796,9 @@ int nmma_b200_mags(nmma_b200_t* h, const double* points_dev, int64_t N, int appa
 int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     if (!h || !key) return NMMA_B200_ERR_ARG;
     const std::string k(key);
-    if (k == "path") { if (value < 0 || value > 2) return fail(h, NMMA_B200_ERR_ARG, "path must be 0, 1 or 2"); h->opt_path = (int)value; }
+    if (k == "path") { if (value < 0 || value > 3) return fail(h, NMMA_B200_ERR_ARG, "path must be 0, 1, 2 or 3"); h->opt_path = (int)value; }
     else if (k == "fused_min_points") h->opt_fused_min = value;
+    else if (k == "tc_min_points") h->opt_tc_min = value;
     else if (k == "max_ctas") h->opt_max_ctas = (int)value;
     else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }
     else if (k == "no_fast_backend") h->opt_no_fast = value ? 1 : 0;
@@ -746,6 +815,7 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
     else if (k == "sm_count") *value = h->sm_count;
     else if (k == "ctas_per_sm") *value = h->last_ctas_per_sm;
     else if (k == "fused_supported") { if (int rc = finalize(h, true)) return rc; *value = h->fused_supported ? 1 : 0; }
+    else if (k == "tc_supported") { if (int rc = finalize(h, true)) return rc; *value = h->tc_supported ? 1 : 0; }
     else if (k == "algorithmic_flop_per_eval") {
         // F * [2 H (d + K) + 2 T K] (MLP) or Ntr*3d + F*K*Ntr*8 + F*2*T*K (GP)
         if (h->kind == 0) *value = (int64_t)h->F * (2LL * h->H * (h->d + h->K) + 2LL * h->T * h->K);

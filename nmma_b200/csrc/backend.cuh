@@ -31,6 +31,9 @@ struct DevCfg {
     // MLP front end
     const float* wpack;   // F*HP*RW: row j = [W1[0..d-1][j], b1[j], W2[j][0..K-1], 0-pad]
     const float* b2;      // F*K
+    // tensor-core front end: per (filter, 32-hidden chunk) 1536 floats = B1hi | B1lo | B2hi | B2lo operand tiles
+    const float* tcpack;  // F*tc_nch*1536
+    int tc_nch;           // chunks per filter (even)
     // GP front end
     const double* gpX;    // Ntr*d
     const double* gpA;    // F*K*Ntr  constant_value * alpha_

@@ -300,6 +300,87 @@ inline size_t fused_smem_bytes(int D, int K, int T, int S, int nobs) {
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Back end of the fused kernels for one (point, model filter): reconstructs only the two grid rows that bracket each
+// observation of the observed filters mapped onto f, interpolates to the observation time (np.interp semantics,
+// em_likelihood.py:313-335) and returns the sum of the per-observation terms (em_likelihood.py:224-256).
+// `bp` = basis pack of filter f, `s_obs` = observation records, `s_samp` = sample grid, all in shared memory.
+template <int K, bool FAST>
+__device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, const double (&cp)[K], const PointScal& ps,
+                                                    const double* __restrict__ row, const double* __restrict__ bp,
+                                                    const double* __restrict__ s_obs, const double* __restrict__ s_samp) {
+    const int lo = cfg.s_lo[f], hi = cfg.s_hi[f];
+    const double z1 = ps.z1, tsh = ps.ts;
+    const double inv_z1 = 1.0 / z1;
+    const double tlo = __dadd_rn(__dmul_rn(s_samp[lo], z1), tsh);
+    const double thi = __dadd_rn(__dmul_rn(s_samp[hi], z1), tsh);
+    double lsum = 0.0;
+    for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
+        const int g = cfg.f_glist[gi];
+        const double lim = cfg.g_lim[g];
+        const int mode = cfg.sy_mode[g];
+        const int k1 = cfg.g_off[g + 1];
+        for (int k = cfg.g_off[g]; k < k1; ++k) {
+            const double* rec = s_obs + k * kObsRec;  // t, mag, sigma_obs, sigma, 1/sigma, log(sigma)+C
+            const double t = rec[0], m = rec[1], so = rec[2];
+            double mu;
+            if constexpr (FAST) {
+                if (t < tlo || t > thi) {
+                    mu = CUDART_INF;  // np.interp left = right = +inf
+                } else {
+                    // interval search: O(1) guess from the inverse map, settled by the exact
+                    // (mul, add) comparisons np.interp's bisection would make
+                    const double gq = (__dsub_rn(t, tsh) * inv_z1 - cfg.uni_s0) * cfg.uni_inv_ds;
+                    int j = (gq >= (double)hi) ? hi : ((gq <= (double)lo) ? lo : (int)gq);
+                    double tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh);
+                    double tj1 = (j < hi) ? __dadd_rn(__dmul_rn(s_samp[j + 1], z1), tsh) : CUDART_INF;
+                    int guard = 0;
+                    while (tj > t && j > lo && guard < 8) {
+                        --j; tj1 = tj; tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh); ++guard;
+                    }
+                    while (j < hi && tj1 <= t && guard < 8) {
+                        ++j; tj = tj1;
+                        tj1 = (j < hi) ? __dadd_rn(__dmul_rn(s_samp[j + 1], z1), tsh) : CUDART_INF;
+                        ++guard;
+                    }
+                    if (!(tj <= t && (j == hi || tj1 > t))) {  // cold: fall back to bisection
+                        j = locate(cfg, lo, hi, t, z1, tsh);
+                        tj = tobs_at(cfg, j, z1, tsh);
+                        tj1 = (j < hi) ? tobs_at(cfg, j + 1, z1, tsh) : CUDART_INF;
+                    }
+                    const double a0 = __dadd_rn(__dadd_rn(node_mag_k<K>(bp, j, cp), ps.dm), ps.zc);
+                    if (j == hi || tj == t) {
+                        mu = a0;
+                    } else {
+                        const double a1 = __dadd_rn(__dadd_rn(node_mag_k<K>(bp, j + 1, cp), ps.dm), ps.zc);
+                        // slope * (t - tj) + a0 with the interpolation weight in fp32: the weight only
+                        // scales (a1 - a0) <~ 1 mag, so its 6e-8 relative error is < 1e-7 mag
+                        const float wgt = __fdividef((float)__dsub_rn(t, tj), (float)__dsub_rn(tj1, tj));
+                        mu = fma(__dsub_rn(a1, a0), (double)wgt, a0);
+                        if (isnan(mu) && a0 == a1) mu = a0;
+                    }
+                }
+            } else {
+                auto node = [&](int j) { return node_mag_k<K>(bp, j, cp); };
+                auto abs_at = [&](int s) { return sample_mag(cfg, f, s, node); };
+                mu = interp_obs(cfg, f, t, ps, abs_at);
+            }
+            double term;
+            if (FAST && mode == 0 && lim == CUDART_INF && isfinite(so)) {
+                // truncnorm.logpdf with b = +inf: NaN when mu is +inf/NaN (b = inf - inf), else the
+                // plain Gaussian log-density with the staged 1/sigma and log(sigma) + log(2 pi)/2
+                const double xq = __dsub_rn(m, mu) * rec[4];
+                term = (mu < CUDART_INF) ? (-0.5 * (xq * xq) - rec[5]) : CUDART_NAN;
+            } else if (mode == 0 && isfinite(so)) {
+                term = obs_term_static_det(m, mu, rec[3], rec[5], lim);
+            } else {
+                term = obs_term(m, mu, so, sys_sigma(cfg, g, t, row), lim);
+            }
+            lsum += term;
+        }
+    }
+    return lsum;
+}
+
 // FAST = sample grid is the (uniform) training grid itself: stage 1 is the identity and the
 // interval search starts from an O(1) guess.
 template <int D, int K, int PT, bool FAST>
@@ -458,8 +539,6 @@ fused_mlp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long lon
             }
             // ---- back end for the observed filters that map onto f ----
             mbar_wait(full_b, (uint32_t)(qb & 1));
-            const double* bp = s_basis;
-            const int lo = cfg.s_lo[f], hi = cfg.s_hi[f];
 #pragma unroll
             for (int p = 0; p < PT; ++p) {
                 // coefficients: + b2 in fp32 (Keras Dense), then fp64 for the rest
@@ -471,77 +550,8 @@ fused_mlp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long lon
                     cp[k] = (double)cf;
                 }
                 if (!ok[p]) continue;
-                const double z1 = ps[p].z1, tsh = ps[p].ts;
-                const double inv_z1 = 1.0 / z1;
-                const double tlo = __dadd_rn(__dmul_rn(s_samp[lo], z1), tsh);
-                const double thi = __dadd_rn(__dmul_rn(s_samp[hi], z1), tsh);
-                double lsum = 0.0;
-                for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
-                    const int g = cfg.f_glist[gi];
-                    const double lim = cfg.g_lim[g];
-                    const int mode = cfg.sy_mode[g];
-                    const int k1 = cfg.g_off[g + 1];
-                    for (int k = cfg.g_off[g]; k < k1; ++k) {
-                        const double* rec = s_obs + k * kObsRec;  // t, mag, sigma_obs, sigma, 1/sigma, log(sigma)+C
-                        const double t = rec[0], m = rec[1], so = rec[2];
-                        double mu;
-                        if constexpr (FAST) {
-                            if (t < tlo || t > thi) {
-                                mu = CUDART_INF;  // np.interp left = right = +inf
-                            } else {
-                                // interval search: O(1) guess from the inverse map, settled by the exact
-                                // (mul, add) comparisons np.interp's bisection would make
-                                const double gq = (__dsub_rn(t, tsh) * inv_z1 - cfg.uni_s0) * cfg.uni_inv_ds;
-                                int j = (gq >= (double)hi) ? hi : ((gq <= (double)lo) ? lo : (int)gq);
-                                double tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh);
-                                double tj1 = (j < hi) ? __dadd_rn(__dmul_rn(s_samp[j + 1], z1), tsh) : CUDART_INF;
-                                int guard = 0;
-                                while (tj > t && j > lo && guard < 8) {
-                                    --j; tj1 = tj; tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh); ++guard;
-                                }
-                                while (j < hi && tj1 <= t && guard < 8) {
-                                    ++j; tj = tj1;
-                                    tj1 = (j < hi) ? __dadd_rn(__dmul_rn(s_samp[j + 1], z1), tsh) : CUDART_INF;
-                                    ++guard;
-                                }
-                                if (!(tj <= t && (j == hi || tj1 > t))) {  // cold: fall back to bisection
-                                    j = locate(cfg, lo, hi, t, z1, tsh);
-                                    tj = tobs_at(cfg, j, z1, tsh);
-                                    tj1 = (j < hi) ? tobs_at(cfg, j + 1, z1, tsh) : CUDART_INF;
-                                }
-                                const double a0 = __dadd_rn(__dadd_rn(node_mag_k<K>(bp, j, cp), ps[p].dm), ps[p].zc);
-                                if (j == hi || tj == t) {
-                                    mu = a0;
-                                } else {
-                                    const double a1 = __dadd_rn(__dadd_rn(node_mag_k<K>(bp, j + 1, cp), ps[p].dm), ps[p].zc);
-                                    // slope * (t - tj) + a0 with the interpolation weight in fp32: the weight only
-                                    // scales (a1 - a0) <~ 1 mag, so its 6e-8 relative error is < 1e-7 mag
-                                    const float wgt = __fdividef((float)__dsub_rn(t, tj), (float)__dsub_rn(tj1, tj));
-                                    mu = fma(__dsub_rn(a1, a0), (double)wgt, a0);
-                                    if (isnan(mu) && a0 == a1) mu = a0;
-                                }
-                            }
-                        } else {
-                            auto node = [&](int j) { return node_mag_k<K>(bp, j, cp); };
-                            auto abs_at = [&](int s) { return sample_mag(cfg, f, s, node); };
-                            mu = interp_obs(cfg, f, t, ps[p], abs_at);
-                        }
-                        double term;
-                        if (FAST && mode == 0 && lim == CUDART_INF && isfinite(so)) {
-                            // truncnorm.logpdf with b = +inf: NaN when mu is +inf/NaN (b = inf - inf), else the
-                            // plain Gaussian log-density with the staged 1/sigma and log(sigma) + log(2 pi)/2
-                            const double xq = __dsub_rn(m, mu) * rec[4];
-                            term = (mu < CUDART_INF) ? (-0.5 * (xq * xq) - rec[5]) : CUDART_NAN;
-                        } else if (mode == 0 && isfinite(so)) {
-                            term = obs_term_static_det(m, mu, rec[3], rec[5], lim);
-                        } else {
-                            const double* row = pts + (live[p] ? n[p] : 0) * cfg.P;
-                            term = obs_term(m, mu, so, sys_sigma(cfg, g, t, row), lim);
-                        }
-                        lsum += term;
-                    }
-                }
-                logl[p] += lsum;
+                logl[p] += fused_filter_logl<K, FAST>(cfg, f, cp, ps[p], pts + (live[p] ? n[p] : 0) * cfg.P, s_basis, s_obs,
+                                                      s_samp);
             }
             // release the basis pack; the last warp to arrive loads the next filter's pack
             __syncwarp();

@@ -1,0 +1,391 @@
+// Tensor-core throughput kernel: the surrogate MLP on tcgen05 (5th-gen tensor cores, accumulators and the
+// activation operand in TMEM), 3xTF32 split precision, fused with the fp64 likelihood back end.
+//
+// Why split precision: single-pass TF32/BF16 misses the 1e-3 mag budget by two orders of magnitude
+// (profiles/r01_tc_numerics.txt); with a = a_hi + a_lo, b = b_hi + b_lo (hi = top 19 bits, which is exactly what the
+// tensor core reads from an fp32 operand of kind::tf32) the three products a_hi*b_hi + a_lo*b_hi + a_hi*b_lo carry
+// ~2^-21 relative error, the same order as fp32 FFMA.  The tensor core adds into its fp32 accumulator with
+// round-toward-zero (profiles/r01_tc_probe.txt), so accumulation chains are kept to one 32-hidden chunk (12 MMAs)
+// and the chunk partials are summed by the CUDA cores with round-to-nearest adds.
+//
+// Work decomposition (one persistent CTA per SM, 320 threads):
+//   warps 0-3 / 4-7  "point" warps of tile 0 / tile 1: thread = one parameter point = one TMEM lane.  Per filter they
+//                    write the scaled inputs as the layer-1 A operand (TMEM), then per 32-hidden chunk read the
+//                    layer-1 accumulator (tcgen05.ld), apply ReLU, split into hi/lo and write the layer-2 A operand
+//                    back to TMEM (tcgen05.st), sum the layer-2 chunk partials, and finally run the fp64 back end.
+//   warp 8           MMA issuer (one elected lane):  D1 = [x_hi,1 | x_lo] . [W1;b1]^T  (3 MMAs, 128x32x8) and
+//                    D2 = [h_hi | h_lo] . W2^T (12 MMAs, 128x16x8) per chunk and tile, A from TMEM, B from smem.
+//   warp 9           TMA producer: 6 KB weight chunks (cp.async.bulk) into a shared-memory ring, basis packs per filter.
+// All hand-offs are mbarriers (tcgen05.commit for MMA completion); nothing spins on memory.
+#pragma once
+#include "kernels.cuh"
+
+namespace nmma {
+
+constexpr int kTcThreads = 320;
+constexpr int kTcPointWarps = 8;
+constexpr int kTcTile = 128;                 // points per tile = TMEM lanes
+constexpr int kTcTiles = 2;                  // tiles in flight per CTA
+constexpr int kTcChunk = 32;                 // hidden units per chunk
+constexpr int kTcChunkFloats = 1536;         // B1hi 256 | B1lo 256 | B2hi 512 | B2lo 512
+constexpr uint32_t kTcChunkBytes = kTcChunkFloats * 4;
+constexpr int kTcStages = 12;                // weight ring depth (72 KB)
+constexpr int kTcN2 = 16;                    // layer-2 MMA N (n_coeff padded)
+// TMEM columns of one tile (tile t at column 256 t)
+constexpr uint32_t kColD1 = 0;               // 2 x 32  layer-1 accumulators
+constexpr uint32_t kColA2H = 64;             // 2 x 32  relu(h) (the tensor core reads its top 19 bits = h_hi)
+constexpr uint32_t kColA2L = 128;            // 2 x 32  h_lo
+constexpr uint32_t kColD2 = 192;             // 2 x 16  layer-2 chunk partials
+constexpr uint32_t kColA1H = 224;            // 8       [x_hi, 1, 0..]
+constexpr uint32_t kColA1L = 232;            // 8       [x_lo, 0, 0..]
+
+// ---- tcgen05 wrappers (PTX forms as in cute/arch/mma_sm100_umma.hpp, copy_sm100.hpp, tmem_allocator_sm100.hpp) ----
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::tf32, M = 128
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(addr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(addr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(addr)
+        : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1): core matrix = 8 rows of
+// 16 B, rows 16 B apart; lbo = bytes between the two 16-byte K halves, sbo = bytes between 8-row groups.
+__host__ __device__ inline uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// kind::tf32 instruction descriptor: fp32 accumulate, A/B tf32, both K-major, M = 128 (cute::UMMA::InstrDescriptor).
+__host__ __device__ constexpr uint32_t tc_idesc(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+// float index of element (n, k) of an N x 8 B-operand tile
+__host__ __device__ constexpr int tc_b_index(int N, int n, int k) { return (k >> 2) * (N * 4) + n * 4 + (k & 3); }
+
+__host__ __device__ inline size_t tc_smem_bytes(int K, int T, int S, int nobs) {
+    const size_t w = (size_t)kTcStages * kTcChunkBytes;
+    const size_t o = ((size_t)nobs * kObsRec * sizeof(double) + 127) / 128 * 128;
+    const size_t sg = ((size_t)S * sizeof(double) + 127) / 128 * 128;
+    return w + 2 * fused_bslot(K, T) + o + sg + 512 /* barriers, tmem base */;
+}
+
+struct TcBars {
+    uint64_t w_full[kTcStages], w_free[kTcStages];
+    uint64_t b_full[2], b_free[2];
+    uint64_t a1_full[kTcTiles];
+    uint64_t d1_full[kTcTiles][2], d1_free[kTcTiles][2];
+    uint64_t a2_full[kTcTiles][2], a2_free[kTcTiles][2];
+    uint32_t tmem_base;
+};
+
+template <int K, bool FAST>
+__global__ void __launch_bounds__(kTcThreads, 1)
+fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ out) {
+    static_assert(K <= kTcN2, "n_coeff must fit the N=16 layer-2 MMA");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const size_t wbytes = (size_t)kTcStages * kTcChunkBytes;
+    const size_t bslot = fused_bslot(K, cfg.T);
+    const uint32_t bbytes = (uint32_t)(cfg.T * (K + 2) * sizeof(double));
+    const size_t obytes = ((size_t)cfg.nobs * kObsRec * sizeof(double) + 127) / 128 * 128;
+    const size_t sbytes = ((size_t)cfg.S * sizeof(double) + 127) / 128 * 128;
+    float* wring = reinterpret_cast<float*>(smem);
+    unsigned char* s_basis0 = smem + wbytes;
+    double* s_obs = reinterpret_cast<double*>(smem + wbytes + 2 * bslot);
+    double* s_samp = reinterpret_cast<double*>(smem + wbytes + 2 * bslot + obytes);
+    TcBars* bars = reinterpret_cast<TcBars*>(smem + wbytes + 2 * bslot + obytes + sbytes);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F = cfg.F, NCH = cfg.tc_nch;
+    constexpr int SUPER = kTcTile * kTcTiles;
+    const long long nsuper = (N + SUPER - 1) / SUPER;
+    const long long my_super = (nsuper > blockIdx.x) ? (nsuper - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int i = 0; i < kTcStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_free[i], kTcPointWarps); }
+        for (int t = 0; t < kTcTiles; ++t) {
+            mbar_init(&bars->a1_full[t], 4);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&bars->d1_full[t][b], 1);
+                mbar_init(&bars->d1_free[t][b], 4);
+                mbar_init(&bars->a2_full[t][b], 4);
+                mbar_init(&bars->a2_free[t][b], 1);
+            }
+        }
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc(&bars->tmem_base, 512);
+    for (int i = tid; i < cfg.nobs * kObsRec; i += kTcThreads) s_obs[i] = cfg.o_pack[i];
+    for (int i = tid; i < cfg.S; i += kTcThreads) s_samp[i] = cfg.samp[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp < kTcPointWarps) {
+        // =====================================================================================================
+        // point warps
+        // =====================================================================================================
+        const int t = warp >> 2;
+        const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(256 * t);
+        long long vseq = 0;  // (super-tile, filter) sequence number of this CTA
+        for (long long it = 0; it < my_super; ++it) {
+            const long long sup = blockIdx.x + it * gridDim.x;
+            const long long n = sup * SUPER + (long long)t * kTcTile + (warp & 3) * 32 + lane;
+            const bool live = n < N;
+            const double* row = pts + (live ? n : 0) * cfg.P;
+            const PointScal ps = point_setup(cfg, row);
+            bool ok = !ps.bad && !cfg.static_fail;
+            double logl = 0.0;
+            for (int f = 0; f < F; ++f, ++vseq) {
+                // ---- layer-1 A operand: [x_hi, 1, 0.. | x_lo, 0, 0..] (fp64 scaling, fp32 cast like Keras) ----
+                {
+                    uint32_t ah[8], al[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float xv = 0.f;
+                        if (i < cfg.d) {
+                            const double xs = scaled_input(cfg, f, i, row);
+                            ok = ok && isfinite(xs);
+                            xv = (float)xs;
+                        } else if (i == cfg.d) {
+                            xv = 1.0f;
+                        }
+                        const float xh = __uint_as_float(__float_as_uint(xv) & 0xFFFFE000u);
+                        ah[i] = __float_as_uint(xv);
+                        al[i] = __float_as_uint(xv - xh);
+                    }
+                    tmem_st8(tbase + kColA1H, ah);
+                    tmem_st8(tbase + kColA1L, al);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->a1_full[t]);
+                }
+                float acc[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = 0.f;
+                const long long gbase = vseq * NCH;  // NCH is even: buffer = c & 1, use count = (gbase + c) >> 1
+                for (int c = 0; c < NCH; ++c) {
+                    const int b = c & 1;
+                    const uint32_t u = (uint32_t)((gbase + c) >> 1);
+                    uint32_t v[32], lo[32];
+                    mbar_wait(&bars->d1_full[t][b], u & 1);
+                    tc_fence_after();
+                    tmem_ld32(tbase + kColD1 + 32 * b, v);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->d1_free[t][b]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float h = fmaxf(__uint_as_float(v[j]), 0.f);
+                        const float hh = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
+                        v[j] = __float_as_uint(h);
+                        lo[j] = __float_as_uint(h - hh);
+                    }
+                    if (c >= 2) {
+                        // L2 of chunk c-2 done: its A2 buffer is free and its partial sits in D2[b]
+                        mbar_wait(&bars->a2_free[t][b], (u - 1) & 1);
+                        tc_fence_after();
+                        uint32_t part[16];
+                        tmem_ld16(tbase + kColD2 + 16 * b, part);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
+                    }
+                    tmem_st32(tbase + kColA2H + 32 * b, v);
+                    tmem_st32(tbase + kColA2L + 32 * b, lo);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->a2_full[t][b]);
+                }
+                // drain the last two partials
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const uint32_t u = (uint32_t)((gbase + NCH - 2 + b) >> 1);
+                    mbar_wait(&bars->a2_free[t][b], u & 1);
+                    tc_fence_after();
+                    uint32_t part[16];
+                    tmem_ld16(tbase + kColD2 + 16 * b, part);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
+                }
+                tc_fence_before();
+                // ---- fp64 back end for the observed filters mapped onto f ----
+                const int slot = (int)(vseq & 1);
+                mbar_wait(&bars->b_full[slot], (uint32_t)((vseq >> 1) & 1));
+                double cp[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float cf = acc[k] + cfg.b2[f * K + k];
+                    ok = ok && isfinite(cf);
+                    cp[k] = (double)cf;
+                }
+                if (ok)
+                    logl += fused_filter_logl<K, FAST>(cfg, f, cp, ps, row,
+                                                       reinterpret_cast<const double*>(s_basis0 + slot * bslot), s_obs, s_samp);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->b_free[slot]);
+            }
+            if (live) out[n] = (ok && isfinite(logl)) ? logl : NMMA_SENTINEL;
+        }
+    } else if (warp == 8) {
+        // =====================================================================================================
+        // MMA issuer
+        // =====================================================================================================
+        constexpr uint32_t id1 = tc_idesc(kTcChunk), id2 = tc_idesc(kTcN2);
+        const uint32_t wbase = smem_u32(wring);
+        long long q = 0;     // weight-chunk sequence number (ring position)
+        long long vseq = 0;
+        auto issue_l1 = [&](int t, int c, long long qc) {  // D1[t][c&1] = A1 . B1(chunk qc)
+            const int b = c & 1;
+            const uint32_t u = (uint32_t)((vseq * NCH + c) >> 1);
+            mbar_wait(&bars->d1_free[t][b], (u & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sb = wbase + (uint32_t)(qc % kTcStages) * kTcChunkBytes;
+                const uint64_t bh = tc_smem_desc(sb, kTcChunk * 16, 128), bl = tc_smem_desc(sb + 1024, kTcChunk * 16, 128);
+                const uint32_t tb = tmem + 256 * t;
+                mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, bh, id1, 0u);
+                mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1L, bh, id1, 1u);
+                mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, bl, id1, 1u);
+                tc_commit(&bars->d1_full[t][b]);
+            }
+            __syncwarp();
+        };
+        for (long long it = 0; it < my_super; ++it) {
+            for (int f = 0; f < F; ++f, ++vseq) {
+                // prologue: layer 1 of chunks 0 and 1
+                for (int c = 0; c < 2 && c < NCH; ++c) {
+                    mbar_wait(&bars->w_full[(q + c) % kTcStages], (uint32_t)(((q + c) / kTcStages) & 1));
+                    for (int t = 0; t < kTcTiles; ++t) {
+                        if (c == 0) mbar_wait(&bars->a1_full[t], (uint32_t)(vseq & 1));
+                        issue_l1(t, c, q + c);
+                    }
+                }
+                for (int c = 0; c < NCH; ++c) {
+                    const int b = c & 1;
+                    const uint32_t u = (uint32_t)((vseq * NCH + c) >> 1);
+                    if (c + 2 < NCH)
+                        mbar_wait(&bars->w_full[(q + c + 2) % kTcStages], (uint32_t)(((q + c + 2) / kTcStages) & 1));
+                    for (int t = 0; t < kTcTiles; ++t) {
+                        mbar_wait(&bars->a2_full[t][b], u & 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t sb = wbase + (uint32_t)((q + c) % kTcStages) * kTcChunkBytes;
+                            const uint32_t tb = tmem + 256 * t;
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                const uint64_t bh = tc_smem_desc(sb + 2048 + s * 512, kTcN2 * 16, 128);
+                                const uint64_t bl = tc_smem_desc(sb + 4096 + s * 512, kTcN2 * 16, 128);
+                                mma_tf32_ts(tb + kColD2 + 16 * b, tb + kColA2H + 32 * b + 8 * s, bh, id2, s > 0 ? 1u : 0u);
+                                mma_tf32_ts(tb + kColD2 + 16 * b, tb + kColA2L + 32 * b + 8 * s, bh, id2, 1u);
+                                mma_tf32_ts(tb + kColD2 + 16 * b, tb + kColA2H + 32 * b + 8 * s, bl, id2, 1u);
+                            }
+                            tc_commit(&bars->a2_free[t][b]);
+                            if (t == kTcTiles - 1) tc_commit(&bars->w_free[(q + c) % kTcStages]);
+                        }
+                        __syncwarp();
+                        if (c + 2 < NCH) issue_l1(t, c + 2, q + c + 2);
+                    }
+                }
+                q += NCH;
+            }
+        }
+    } else {
+        // =====================================================================================================
+        // TMA producer
+        // =====================================================================================================
+        long long q = 0, vseq = 0;
+        for (long long it = 0; it < my_super; ++it) {
+            for (int f = 0; f < F; ++f, ++vseq) {
+                const int slot = (int)(vseq & 1);
+                mbar_wait(&bars->b_free[slot], (uint32_t)(((vseq >> 1) & 1) ^ 1));
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bars->b_full[slot], bbytes);
+                    bulk_g2s(s_basis0 + slot * bslot, cfg.bpack + (size_t)f * cfg.T * (K + 2), bbytes, &bars->b_full[slot]);
+                }
+                __syncwarp();
+                for (int c = 0; c < NCH; ++c, ++q) {
+                    const int st = (int)(q % kTcStages);
+                    mbar_wait(&bars->w_free[st], (uint32_t)(((q / kTcStages) & 1) ^ 1));
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&bars->w_full[st], kTcChunkBytes);
+                        bulk_g2s(wring + (size_t)st * kTcChunkFloats,
+                                 cfg.tcpack + ((size_t)f * NCH + c) * kTcChunkFloats, kTcChunkBytes, &bars->w_full[st]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace nmma
