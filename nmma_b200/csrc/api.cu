@@ -166,12 +166,14 @@ int launch_fused_d(nmma_b200_t* h, const double* pts, long long N, double* out, 
 
 int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
     switch (h->d) {
+#ifndef NMMA_DEV_BUILD  // development builds instantiate d = 4 only (compile time)
         case 2: return launch_fused_d<2>(h, pts, N, out, st);
         case 3: return launch_fused_d<3>(h, pts, N, out, st);
-        case 4: return launch_fused_d<4>(h, pts, N, out, st);
         case 5: return launch_fused_d<5>(h, pts, N, out, st);
         case 6: return launch_fused_d<6>(h, pts, N, out, st);
         case 7: return launch_fused_d<7>(h, pts, N, out, st);
+#endif
+        case 4: return launch_fused_d<4>(h, pts, N, out, st);
         default: return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused kernel not instantiated for d=%d", h->d);
     }
 }

@@ -8,22 +8,28 @@
 // round-toward-zero (profiles/r01_tc_probe.txt), so accumulation chains are kept to one 32-hidden chunk (12 MMAs)
 // and the chunk partials are summed by the CUDA cores with round-to-nearest adds.
 //
-// Work decomposition (one persistent CTA per SM, 320 threads):
-//   warps 0-3 / 4-7  "point" warps of tile 0 / tile 1: thread = one parameter point = one TMEM lane.  Per filter they
-//                    write the scaled inputs as the layer-1 A operand (TMEM), then per 32-hidden chunk read the
-//                    layer-1 accumulator (tcgen05.ld), apply ReLU, split into hi/lo and write the layer-2 A operand
-//                    back to TMEM (tcgen05.st), sum the layer-2 chunk partials, and finally run the fp64 back end.
-//   warp 8           MMA issuer (one elected lane):  D1 = [x_hi,1 | x_lo] . [W1;b1]^T  (3 MMAs, 128x32x8) and
-//                    D2 = [h_hi | h_lo] . W2^T (12 MMAs, 128x16x8) per chunk and tile, A from TMEM, B from smem.
-//   warp 9           TMA producer: 6 KB weight chunks (cp.async.bulk) into a shared-memory ring, basis packs per filter.
+// Work decomposition (one persistent CTA per SM, 20 warps, two 128-point tiles in flight):
+//   warps 0-3 / 4-7    activation warps of tile 0 / 1: thread = one parameter point = one TMEM lane.  Per filter they
+//                      write the scaled inputs as the layer-1 A operand (TMEM); per 32-hidden chunk they read the
+//                      layer-1 accumulator (tcgen05.ld), apply ReLU, split into hi/lo, write the layer-2 A operand back
+//                      to TMEM (tcgen05.st) and sum the layer-2 chunk partials; the K coefficients go to shared memory.
+//   warps 8 / 9        MMA issuer of tile 0 / 1 (one elected lane): per chunk D2 = [h_hi | h_lo] . W2^T (12 MMAs,
+//                      128x16x8) and, two chunks ahead, D1 = [x_hi,1 | x_lo] . [W1;b1]^T (3 MMAs, 128x32x8); A from
+//                      TMEM, B from shared memory.
+//   warp 10            TMA producer: 6 KB weight chunks (cp.async.bulk) into a shared-memory ring, basis packs per filter.
+//   warp 11            TMEM allocation / release.
+//   warps 12-15/16-19  back-end warps of tile 0 / 1: thread = one point; fp64 reconstruction, interpolation and
+//                      likelihood for the filter whose coefficients the activation warps just finished, overlapping
+//                      the next filter's MLP.
 // All hand-offs are mbarriers (tcgen05.commit for MMA completion); nothing spins on memory.
 #pragma once
 #include "kernels.cuh"
 
 namespace nmma {
 
-constexpr int kTcThreads = 320;
-constexpr int kTcPointWarps = 8;
+constexpr int kTcThreads = 640;
+constexpr int kTcActWarps = 8;
+constexpr int kTcBackWarp0 = 12;
 constexpr int kTcTile = 128;                 // points per tile = TMEM lanes
 constexpr int kTcTiles = 2;                  // tiles in flight per CTA
 constexpr int kTcChunk = 32;                 // hidden units per chunk
@@ -63,14 +69,16 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-// D[tmem] (+)= A[tmem] . B[smem]^T, kind::tf32, M = 128
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::tf32, M = 128.  The matrix descriptor is passed as two 32-bit halves: only
+// the low half (start address) changes between MMAs, so the issuer's address arithmetic stays 32-bit.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -123,19 +131,21 @@ __host__ __device__ constexpr uint32_t tc_idesc(int N) {
 // float index of element (n, k) of an N x 8 B-operand tile
 __host__ __device__ constexpr int tc_b_index(int N, int n, int k) { return (k >> 2) * (N * 4) + n * 4 + (k & 3); }
 
+__host__ __device__ inline size_t tc_cbuf_bytes() { return (size_t)kTcTiles * 2 * kTcN2 * kTcTile * sizeof(float); }
 __host__ __device__ inline size_t tc_smem_bytes(int K, int T, int S, int nobs) {
     const size_t w = (size_t)kTcStages * kTcChunkBytes;
     const size_t o = ((size_t)nobs * kObsRec * sizeof(double) + 127) / 128 * 128;
     const size_t sg = ((size_t)S * sizeof(double) + 127) / 128 * 128;
-    return w + 2 * fused_bslot(K, T) + o + sg + 512 /* barriers, tmem base */;
+    return w + 2 * fused_bslot(K, T) + o + sg + tc_cbuf_bytes() + 512 /* barriers, tmem base */;
 }
 
 struct TcBars {
     uint64_t w_full[kTcStages], w_free[kTcStages];
     uint64_t b_full[2], b_free[2];
     uint64_t a1_full[kTcTiles];
-    uint64_t d1_full[kTcTiles][2], d1_free[kTcTiles][2];
+    uint64_t d1_full[kTcTiles][2];
     uint64_t a2_full[kTcTiles][2], a2_free[kTcTiles][2];
+    uint64_t c_full[kTcTiles][2], c_free[kTcTiles][2];
     uint32_t tmem_base;
 };
 
@@ -153,29 +163,32 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
     unsigned char* s_basis0 = smem + wbytes;
     double* s_obs = reinterpret_cast<double*>(smem + wbytes + 2 * bslot);
     double* s_samp = reinterpret_cast<double*>(smem + wbytes + 2 * bslot + obytes);
-    TcBars* bars = reinterpret_cast<TcBars*>(smem + wbytes + 2 * bslot + obytes + sbytes);
+    float* s_c = reinterpret_cast<float*>(smem + wbytes + 2 * bslot + obytes + sbytes);  // [tile][slot][k][point]
+    TcBars* bars = reinterpret_cast<TcBars*>(smem + wbytes + 2 * bslot + obytes + sbytes + tc_cbuf_bytes());
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int F = cfg.F, NCH = cfg.tc_nch;
     constexpr int SUPER = kTcTile * kTcTiles;
     const long long nsuper = (N + SUPER - 1) / SUPER;
     const long long my_super = (nsuper > blockIdx.x) ? (nsuper - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t half = (uint32_t)NCH >> 1;  // NCH is even: TMEM buffer = c & 1, its use count = vseq * half + (c >> 1)
 
     if (tid == 0) {
-        for (int i = 0; i < kTcStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_free[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_free[i], kTcPointWarps); }
+        for (int i = 0; i < kTcStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_free[i], kTcTiles); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_free[i], 8); }
         for (int t = 0; t < kTcTiles; ++t) {
             mbar_init(&bars->a1_full[t], 4);
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&bars->d1_full[t][b], 1);
-                mbar_init(&bars->d1_free[t][b], 4);
                 mbar_init(&bars->a2_full[t][b], 4);
                 mbar_init(&bars->a2_free[t][b], 1);
+                mbar_init(&bars->c_full[t][b], 4);
+                mbar_init(&bars->c_free[t][b], 4);
             }
         }
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(&bars->tmem_base, 512);
+    if (warp == 11) tmem_alloc(&bars->tmem_base, 512);
     for (int i = tid; i < cfg.nobs * kObsRec; i += kTcThreads) s_obs[i] = cfg.o_pack[i];
     for (int i = tid; i < cfg.S; i += kTcThreads) s_samp[i] = cfg.samp[i];
     tc_fence_before();
@@ -183,23 +196,21 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp < kTcPointWarps) {
+    if (warp < kTcActWarps) {
         // =====================================================================================================
-        // point warps
+        // activation warps
         // =====================================================================================================
         const int t = warp >> 2;
+        const int pidx = (warp & 3) * 32 + lane;
         const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(256 * t);
-        long long vseq = 0;  // (super-tile, filter) sequence number of this CTA
+        uint32_t vseq = 0;  // (super-tile, filter) sequence number of this CTA
         for (long long it = 0; it < my_super; ++it) {
             const long long sup = blockIdx.x + it * gridDim.x;
-            const long long n = sup * SUPER + (long long)t * kTcTile + (warp & 3) * 32 + lane;
-            const bool live = n < N;
-            const double* row = pts + (live ? n : 0) * cfg.P;
-            const PointScal ps = point_setup(cfg, row);
-            bool ok = !ps.bad && !cfg.static_fail;
-            double logl = 0.0;
+            const long long n = sup * SUPER + (long long)t * kTcTile + pidx;
+            const double* row = pts + (n < N ? n : 0) * cfg.P;
             for (int f = 0; f < F; ++f, ++vseq) {
                 // ---- layer-1 A operand: [x_hi, 1, 0.. | x_lo, 0, 0..] (fp64 scaling, fp32 cast like Keras) ----
+                bool okx = true;
                 {
                     uint32_t ah[8], al[8];
 #pragma unroll
@@ -207,7 +218,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                         float xv = 0.f;
                         if (i < cfg.d) {
                             const double xs = scaled_input(cfg, f, i, row);
-                            ok = ok && isfinite(xs);
+                            okx = okx && isfinite(xs);
                             xv = (float)xs;
                         } else if (i == cfg.d) {
                             xv = 1.0f;
@@ -226,18 +237,16 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 float acc[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) acc[k] = 0.f;
-                const long long gbase = vseq * NCH;  // NCH is even: buffer = c & 1, use count = (gbase + c) >> 1
+                const uint32_t ubase = vseq * half;
+#pragma unroll 2
                 for (int c = 0; c < NCH; ++c) {
                     const int b = c & 1;
-                    const uint32_t u = (uint32_t)((gbase + c) >> 1);
+                    const uint32_t u = ubase + ((uint32_t)c >> 1);
                     uint32_t v[32], lo[32];
                     mbar_wait(&bars->d1_full[t][b], u & 1);
                     tc_fence_after();
                     tmem_ld32(tbase + kColD1 + 32 * b, v);
                     tmem_wait_ld();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->d1_free[t][b]);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float h = fmaxf(__uint_as_float(v[j]), 0.f);
@@ -258,15 +267,14 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     tmem_st32(tbase + kColA2H + 32 * b, v);
                     tmem_st32(tbase + kColA2L + 32 * b, lo);
                     tmem_wait_st();
-                    tc_fence_before();
+                    tc_fence_before();  // orders the D1 / D2 loads and the A2 stores before the issuer's next MMAs
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->a2_full[t][b]);
                 }
                 // drain the last two partials
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    const uint32_t u = (uint32_t)((gbase + NCH - 2 + b) >> 1);
-                    mbar_wait(&bars->a2_free[t][b], u & 1);
+                    mbar_wait(&bars->a2_free[t][b], (ubase + half - 1) & 1);
                     tc_fence_after();
                     uint32_t part[16];
                     tmem_ld16(tbase + kColD2 + 16 * b, part);
@@ -275,16 +283,135 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
                 }
                 tc_fence_before();
-                // ---- fp64 back end for the observed filters mapped onto f ----
+                // ---- hand the coefficients (+ b2 in fp32, Keras Dense) to the back-end warps ----
                 const int slot = (int)(vseq & 1);
-                mbar_wait(&bars->b_full[slot], (uint32_t)((vseq >> 1) & 1));
+                mbar_wait(&bars->c_free[t][slot], ((vseq >> 1) & 1) ^ 1);
+                float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
+#pragma unroll
+                for (int k = 0; k < K; ++k) cb[k * kTcTile] = okx ? acc[k] + cfg.b2[f * K + k] : CUDART_NAN_F;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->c_full[t][slot]);
+            }
+        }
+    } else if (warp < kTcActWarps + kTcTiles) {
+        // =====================================================================================================
+        // MMA issuer of tile t.  Ring cursors advance incrementally; descriptors differ only in their low word.
+        // =====================================================================================================
+        const int t = warp - kTcActWarps;
+        constexpr uint32_t id1 = tc_idesc(kTcChunk), id2 = tc_idesc(kTcN2);
+        const uint32_t wbase = smem_u32(wring);
+        const uint64_t dB1 = tc_smem_desc(wbase, kTcChunk * 16, 128);
+        const uint64_t dB2 = tc_smem_desc(wbase + 2048, kTcN2 * 16, 128);
+        const uint32_t hi1 = (uint32_t)(dB1 >> 32), hi2 = (uint32_t)(dB2 >> 32);
+        constexpr uint32_t kSlotStep = kTcChunkBytes >> 4;
+        uint32_t s1 = 0, p1 = 0;                    // ring slot / phase parity of the next chunk layer 1 consumes
+        uint32_t lo1 = (uint32_t)dB1;               // low descriptor word of that slot's B1hi tile
+        uint32_t s2 = 0, lo2 = (uint32_t)dB2;       // ... layer 2 (its chunk was waited for by layer 1 two chunks earlier)
+        const uint32_t tb = tmem + 256 * t;
+        auto adv1 = [&]() { lo1 += kSlotStep; if (++s1 == kTcStages) { s1 = 0; p1 ^= 1; lo1 = (uint32_t)dB1; } };
+        auto adv2 = [&]() { lo2 += kSlotStep; if (++s2 == kTcStages) { s2 = 0; lo2 = (uint32_t)dB2; } };
+        auto l1 = [&](int b) {  // D1[b] = A1 . B1(slot s1)   (elected lane only)
+            mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, lo1, hi1, id1, 0u);
+            mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1L, lo1, hi1, id1, 1u);
+            mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, lo1 + (1024 >> 4), hi1, id1, 1u);
+            tc_commit(&bars->d1_full[t][b]);
+        };
+        uint32_t vseq = 0;
+        const long long total_v = my_super * F;
+        for (long long vv = 0; vv < total_v; ++vv, ++vseq) {
+            mbar_wait(&bars->a1_full[t], vseq & 1);
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {  // prologue: layer 1 of chunks 0 and 1
+                mbar_wait(&bars->w_full[s1], p1);
+                tc_fence_after();
+                if (elect_one()) l1(b);
+                __syncwarp();
+                adv1();
+            }
+            const uint32_t ubase = vseq * half;
+            for (int c = 0; c < NCH; c += 2) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const bool more = c + b + 2 < NCH;
+                    if (more) mbar_wait(&bars->w_full[s1], p1);
+                    mbar_wait(&bars->a2_full[t][b], (ubase + ((uint32_t)c >> 1)) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d2 = tb + kColD2 + 16 * b, ah = tb + kColA2H + 32 * b, al = tb + kColA2L + 32 * b;
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : 0u);
+                            mma_tf32_ts(d2, al + 8 * s, lo2 + s * 32, hi2, id2, 1u);
+                            mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32 + (2048 >> 4), hi2, id2, 1u);
+                        }
+                        tc_commit(&bars->a2_free[t][b]);
+                        tc_commit(&bars->w_free[s2]);
+                        if (more) l1(b);  // the activation warps read D1[b] before they signalled a2_full[b]
+                    }
+                    __syncwarp();
+                    adv2();
+                    if (more) adv1();
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // =====================================================================================================
+        // TMA producer
+        // =====================================================================================================
+        uint32_t st = 0, ph = 0, vseq = 0;
+        int f = 0;
+        const long long total_v = my_super * F;
+        for (long long vv = 0; vv < total_v; ++vv, ++vseq) {
+            const int slot = (int)(vseq & 1);
+            mbar_wait(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&bars->b_full[slot], bbytes);
+                bulk_g2s(s_basis0 + slot * bslot, cfg.bpack + (size_t)f * cfg.T * (K + 2), bbytes, &bars->b_full[slot]);
+            }
+            __syncwarp();
+            const float* src = cfg.tcpack + (size_t)f * NCH * kTcChunkFloats;
+            for (int c = 0; c < NCH; ++c) {
+                mbar_wait(&bars->w_free[st], ph ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bars->w_full[st], kTcChunkBytes);
+                    bulk_g2s(wring + (size_t)st * kTcChunkFloats, src + (size_t)c * kTcChunkFloats, kTcChunkBytes,
+                             &bars->w_full[st]);
+                }
+                __syncwarp();
+                if (++st == kTcStages) { st = 0; ph ^= 1; }
+            }
+            if (++f == F) f = 0;
+        }
+    } else if (warp >= kTcBackWarp0) {
+        // =====================================================================================================
+        // back-end warps: fp64 likelihood of filter f while the tensor cores work on filter f + 1
+        // =====================================================================================================
+        const int t = (warp - kTcBackWarp0) >> 2;
+        const int pidx = ((warp - kTcBackWarp0) & 3) * 32 + lane;
+        uint32_t vseq = 0;
+        for (long long it = 0; it < my_super; ++it) {
+            const long long sup = blockIdx.x + it * gridDim.x;
+            const long long n = sup * SUPER + (long long)t * kTcTile + pidx;
+            const bool live = n < N;
+            const double* row = pts + (live ? n : 0) * cfg.P;
+            const PointScal ps = point_setup(cfg, row);
+            bool ok = !ps.bad && !cfg.static_fail;
+            double logl = 0.0;
+            for (int f = 0; f < F; ++f, ++vseq) {
+                const int slot = (int)(vseq & 1);
+                const uint32_t par = (vseq >> 1) & 1;
+                mbar_wait(&bars->c_full[t][slot], par);
+                const float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
                 double cp[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float cf = acc[k] + cfg.b2[f * K + k];
+                    const float cf = cb[k * kTcTile];
                     ok = ok && isfinite(cf);
                     cp[k] = (double)cf;
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->c_free[t][slot]);
+                mbar_wait(&bars->b_full[slot], par);
                 if (ok)
                     logl += fused_filter_logl<K, FAST>(cfg, f, cp, ps, row,
                                                        reinterpret_cast<const double*>(s_basis0 + slot * bslot), s_obs, s_samp);
@@ -293,99 +420,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             }
             if (live) out[n] = (ok && isfinite(logl)) ? logl : NMMA_SENTINEL;
         }
-    } else if (warp == 8) {
-        // =====================================================================================================
-        // MMA issuer
-        // =====================================================================================================
-        constexpr uint32_t id1 = tc_idesc(kTcChunk), id2 = tc_idesc(kTcN2);
-        const uint32_t wbase = smem_u32(wring);
-        long long q = 0;     // weight-chunk sequence number (ring position)
-        long long vseq = 0;
-        auto issue_l1 = [&](int t, int c, long long qc) {  // D1[t][c&1] = A1 . B1(chunk qc)
-            const int b = c & 1;
-            const uint32_t u = (uint32_t)((vseq * NCH + c) >> 1);
-            mbar_wait(&bars->d1_free[t][b], (u & 1) ^ 1);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t sb = wbase + (uint32_t)(qc % kTcStages) * kTcChunkBytes;
-                const uint64_t bh = tc_smem_desc(sb, kTcChunk * 16, 128), bl = tc_smem_desc(sb + 1024, kTcChunk * 16, 128);
-                const uint32_t tb = tmem + 256 * t;
-                mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, bh, id1, 0u);
-                mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1L, bh, id1, 1u);
-                mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, bl, id1, 1u);
-                tc_commit(&bars->d1_full[t][b]);
-            }
-            __syncwarp();
-        };
-        for (long long it = 0; it < my_super; ++it) {
-            for (int f = 0; f < F; ++f, ++vseq) {
-                // prologue: layer 1 of chunks 0 and 1
-                for (int c = 0; c < 2 && c < NCH; ++c) {
-                    mbar_wait(&bars->w_full[(q + c) % kTcStages], (uint32_t)(((q + c) / kTcStages) & 1));
-                    for (int t = 0; t < kTcTiles; ++t) {
-                        if (c == 0) mbar_wait(&bars->a1_full[t], (uint32_t)(vseq & 1));
-                        issue_l1(t, c, q + c);
-                    }
-                }
-                for (int c = 0; c < NCH; ++c) {
-                    const int b = c & 1;
-                    const uint32_t u = (uint32_t)((vseq * NCH + c) >> 1);
-                    if (c + 2 < NCH)
-                        mbar_wait(&bars->w_full[(q + c + 2) % kTcStages], (uint32_t)(((q + c + 2) / kTcStages) & 1));
-                    for (int t = 0; t < kTcTiles; ++t) {
-                        mbar_wait(&bars->a2_full[t][b], u & 1);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t sb = wbase + (uint32_t)((q + c) % kTcStages) * kTcChunkBytes;
-                            const uint32_t tb = tmem + 256 * t;
-#pragma unroll
-                            for (int s = 0; s < 4; ++s) {
-                                const uint64_t bh = tc_smem_desc(sb + 2048 + s * 512, kTcN2 * 16, 128);
-                                const uint64_t bl = tc_smem_desc(sb + 4096 + s * 512, kTcN2 * 16, 128);
-                                mma_tf32_ts(tb + kColD2 + 16 * b, tb + kColA2H + 32 * b + 8 * s, bh, id2, s > 0 ? 1u : 0u);
-                                mma_tf32_ts(tb + kColD2 + 16 * b, tb + kColA2L + 32 * b + 8 * s, bh, id2, 1u);
-                                mma_tf32_ts(tb + kColD2 + 16 * b, tb + kColA2H + 32 * b + 8 * s, bl, id2, 1u);
-                            }
-                            tc_commit(&bars->a2_free[t][b]);
-                            if (t == kTcTiles - 1) tc_commit(&bars->w_free[(q + c) % kTcStages]);
-                        }
-                        __syncwarp();
-                        if (c + 2 < NCH) issue_l1(t, c + 2, q + c + 2);
-                    }
-                }
-                q += NCH;
-            }
-        }
-    } else {
-        // =====================================================================================================
-        // TMA producer
-        // =====================================================================================================
-        long long q = 0, vseq = 0;
-        for (long long it = 0; it < my_super; ++it) {
-            for (int f = 0; f < F; ++f, ++vseq) {
-                const int slot = (int)(vseq & 1);
-                mbar_wait(&bars->b_free[slot], (uint32_t)(((vseq >> 1) & 1) ^ 1));
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(&bars->b_full[slot], bbytes);
-                    bulk_g2s(s_basis0 + slot * bslot, cfg.bpack + (size_t)f * cfg.T * (K + 2), bbytes, &bars->b_full[slot]);
-                }
-                __syncwarp();
-                for (int c = 0; c < NCH; ++c, ++q) {
-                    const int st = (int)(q % kTcStages);
-                    mbar_wait(&bars->w_free[st], (uint32_t)(((q / kTcStages) & 1) ^ 1));
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(&bars->w_full[st], kTcChunkBytes);
-                        bulk_g2s(wring + (size_t)st * kTcChunkFloats,
-                                 cfg.tcpack + ((size_t)f * NCH + c) * kTcChunkFloats, kTcChunkBytes, &bars->w_full[st]);
-                    }
-                    __syncwarp();
-                }
-            }
-        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == 11) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace nmma
