@@ -126,7 +126,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -228,6 +228,8 @@ def gpu_arm(args):
                          f"(fp32 NumPy MLP standing in for Keras), multiprocessing pool on all host cores",
                "one_core_value": one_core, "cpu_count": os.cpu_count()}
 
+    # nvidia-smi needs ~1 s to start: launch it now, keep the samples that fall inside the timed regions
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
@@ -309,11 +311,9 @@ def gpu_arm(args):
         per = [a.elapsed_time(b) for a, b in evs] if per_launch else None
         return float(t.item()), per, (t0, t1)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = eng.get_info("launches")
     ms_total, per_launch, (w0, w1) = timed(step_device, args.steps, args.warmup, per_launch=True)
     launches = eng.get_info("launches") - l0 - args.warmup
-    clocks = sampler.stop(w0, w1) if sampler else None
 
     # e2e: wall-clock inside the C call includes the copies; device events would miss the host part
     for i in range(max(args.warmup, 3)):
@@ -328,14 +328,20 @@ def gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    w2 = time.perf_counter()
+    clocks = None
+    if sampler:
+        clocks = sampler.stop(w0, w2)          # device-timed loop + e2e loop, both under load
+        if clocks is not None:
+            clocks["window"] = "device-timed steps and e2e steps (contiguous, GPU busy throughout)"
 
     if rank == 0:
         total_pts = M * world
         value = total_pts * args.steps / (ms_total * 1e-3)
         flop = eng.get_info("algorithmic_flop_per_eval")
+        last_path = eng.get_info("last_path")
         kern_ms = float(np.mean(per_launch))
         achieved = M * flop / (kern_ms * 1e-3) / 1e12
-        peak = max(ffma["scalar_tflops"], ffma["packed_tflops"])
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -348,29 +354,49 @@ def gpu_arm(args):
         except Exception:  # noqa: BLE001
             pass
         P = len(cols)
+        ffma_peak = max(ffma["scalar_tflops"], ffma["packed_tflops"])
+        hbm = {"achieved_gbs": M * (P * 8 + 8) / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+               "frac": M * (P * 8 + 8) / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+               "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}
+        if last_path == 3:
+            # tensor-core kernel: tcgen05 kind::tf32 runs at half the bf16 rate (tools/tc_probe.cu: 128*N/256 cycles per
+            # K=8 MMA = 4096 FLOP/clk/SM); the 3xTF32 split and the N=16 / K=8 operand padding make the EXECUTED
+            # tensor FLOPs 4.79x the algorithmic ones -- both are reported, `achieved` stays algorithmic.
+            bf16_peak = peaks.get("bf16_tflops", 1650.0)
+            tf32_peak = bf16_peak / 2.0
+            executed = eng.get_info("tc_executed_flop_per_eval")
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": achieved / tf32_peak,
+                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops / 2 (dense tf32 = half the bf16 rate)" if peaks
+                                        else "fallback 1650 bf16 TFLOP/s / 2"),
+                        "executed_tensor_tflops": M * executed / (kern_ms * 1e-3) / 1e12,
+                        "executed_frac_of_tf32_peak": M * executed / (kern_ms * 1e-3) / 1e12 / tf32_peak,
+                        "executed_tensor_flop_per_eval": executed,
+                        "frac_of_ffma_peak": achieved / ffma_peak}
+        else:
+            roofline = {"bound": "fp32_fma (CUDA cores; neither HBM nor tensor: SURVEY.md 8d)",
+                        "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s", "frac": achieved / ffma_peak,
+                        "peak_source": "FFMA micro-benchmark measured in this run (nmma_b200_ffma_peak); nominal 74.4 TFLOP/s at 1965 MHz",
+                        "frac_of_nominal": achieved / 74.4}
+        roofline.update({"ffma_peak_measured": ffma, "algorithmic_flop_per_eval": flop, "kernel_ms_per_launch": kern_ms,
+                         "hbm": hbm, "traffic": traffic})
+        kname = {1: "fused_mlp_logl_kernel (FFMA)", 2: "two_stage", 3: "fused_tc_logl_kernel (tcgen05 3xTF32)"}.get(last_path, "?")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 MLP (FFMA) / f64 likelihood",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 MLP (3xTF32 split on tcgen05) / f64 likelihood" if last_path == 3 else "f32 MLP (FFMA) / f64 likelihood",
             "data": "synthetic: random-init Bu2019lm-shaped weights, real AT2017gfo photometry",
             "config": {"workload": WORKLOAD, "points_per_gpu_per_step": M, "global_points_per_step": total_pts,
                        "sharding": f"contiguous row blocks x{world}, NCCL all-gather of logL" if world > 1 else "single GPU",
                        "l2": f"inputs rotate through {N_ROTATE} distinct batches ({N_ROTATE * M * P * 8 / 1e6:.0f} MB > 126 MB L2)",
-                       "kernel_path": {1: "fused", 2: "two_stage"}.get(eng.get_info("last_path"), "?")},
+                       "kernel_path": kname},
             "e2e": {"value": total_pts * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": total_pts * P * 8, "d2h_bytes_per_step": total_pts * 8,
                     "api": "EMTransientLikelihood.log_likelihood_batch -> nmma_b200_logl_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "fp32_fma (CUDA cores; neither HBM nor tensor: SURVEY.md 8d)",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": "FFMA micro-benchmark measured in this run (nmma_b200_ffma_peak); nominal 74.4 TFLOP/s at 1965 MHz",
-                         "ffma_peak_measured": ffma, "frac_of_nominal": achieved / 74.4,
-                         "algorithmic_flop_per_eval": flop, "kernel_ms_per_launch": kern_ms,
-                         "hbm": {"achieved_gbs": M * (P * 8 + 8) / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                                 "frac": M * (P * 8 + 8) / (kern_ms * 1e-3) / 1e9 / hbm_peak,
-                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
-                         "traffic": traffic},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "parity_in_run": parity,
         }
@@ -382,7 +408,7 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)

@@ -66,7 +66,7 @@ struct nmma_b200_handle {
     // ---- knobs / counters ----
     int opt_path = 0;
     long long opt_fused_min = 2048;
-    long long opt_tc_min = 1LL << 62;  // tensor-core path: opt-in until measured faster (set_option "tc_min_points")
+    long long opt_tc_min = 32768;     // tensor-core path from one wave of 148 CTAs x 256 points up (set_option "tc_min_points")
     int opt_max_ctas = 0;
     int opt_no_fast = 0;
     int last_ctas_per_sm = 0;
@@ -823,6 +823,10 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
         if (h->kind == 0) *value = (int64_t)h->F * (2LL * h->H * (h->d + h->K) + 2LL * h->T * h->K);
         else if (h->kind == 1) *value = (int64_t)h->Ntr * 3 * h->d + (int64_t)h->F * h->K * h->Ntr * 8 + (int64_t)h->F * 2 * h->T * h->K;
         else return fail(h, NMMA_B200_ERR_STATE, "no surrogate configured");
+    } else if (k == "tc_executed_flop_per_eval") {
+        // tensor-core kernel: per 32-hidden chunk and point 3 layer-1 MMAs (N=32, K=8) + 12 layer-2 MMAs (N=16, K=8)
+        if (int rc = finalize(h, false)) return rc;
+        *value = (int64_t)h->F * h->cfg.tc_nch * (3LL * 2 * kTcChunk * 8 + 12LL * 2 * kTcN2 * 8);
     } else return fail(h, NMMA_B200_ERR_ARG, "unknown info key '%s'", key);
     return NMMA_B200_OK;
 }
