@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "tc_kernel.cuh"
+#include "hy_kernel.cuh"
 
 using namespace nmma;
 
@@ -55,6 +55,7 @@ struct nmma_b200_handle {
     DevCfg cfg{};
     bool fused_supported = false;
     bool tc_supported = false;
+    bool hy_supported = false;
     double* coeff_scratch = nullptr;
     size_t coeff_cap = 0;
     double* stage_in_dev = nullptr;
@@ -67,6 +68,7 @@ struct nmma_b200_handle {
     int opt_path = 0;
     long long opt_fused_min = 2048;
     long long opt_tc_min = 32768;     // tensor-core path from one wave of 148 CTAs x 256 points up (set_option "tc_min_points")
+    long long opt_hy_min = 32768;     // hybrid (FFMA layer 1 + tcgen05 layer 2) kernel: preferred over the TC kernel
     int opt_max_ctas = 0;
     int opt_no_fast = 0;
     int last_ctas_per_sm = 0;
@@ -201,6 +203,37 @@ int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cud
 int launch_tc(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
     const bool fast = h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
     return fast ? launch_tc_f<true>(h, pts, N, out, st) : launch_tc_f<false>(h, pts, N, out, st);
+}
+
+template <int D, bool FAST>
+int launch_hy_df(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
+    constexpr int K = 10;
+    auto kern = fused_hy_logl_kernel<D, K, FAST>;
+    const size_t smem = hy_smem_bytes(D, K, h->T, h->cfg.S, h->cfg.nobs);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nsuper = (N + kHySuper - 1) / kHySuper;
+    long long grid = h->sm_count;  // one CTA per SM: each CTA owns all 512 TMEM columns of its SM
+    if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
+    grid = std::max<long long>(1, std::min(grid, nsuper));
+    kern<<<(unsigned)grid, kHyThreads, smem, st>>>(h->cfg, pts, N, out);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->last_ctas_per_sm = 1;
+    return NMMA_B200_OK;
+}
+
+bool hy_has(int d, int K) { return (d == 3 || d == 4 || d == 7) && K == 10; }
+
+int launch_hy(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
+    const bool fast = h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
+    switch (h->d) {
+#ifndef NMMA_DEV_BUILD
+        case 3: return fast ? launch_hy_df<3, true>(h, pts, N, out, st) : launch_hy_df<3, false>(h, pts, N, out, st);
+        case 7: return fast ? launch_hy_df<7, true>(h, pts, N, out, st) : launch_hy_df<7, false>(h, pts, N, out, st);
+#endif
+        case 4: return fast ? launch_hy_df<4, true>(h, pts, N, out, st) : launch_hy_df<4, false>(h, pts, N, out, st);
+        default: return fail(h, NMMA_B200_ERR_UNSUPPORTED, "hybrid kernel not instantiated for d=%d", h->d);
+    }
 }
 
 // hi = the 19 bits kind::tf32 reads, lo = remainder (exact in fp32; the tensor core truncates it again)
@@ -358,7 +391,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         c.tcpack = nullptr;
         if (d + 1 <= 8 && K <= kTcN2) {
             int nch = (H + kTcChunk - 1) / kTcChunk;
-            nch += nch & 1;
+            nch = (nch + kTcGroup - 1) / kTcGroup * kTcGroup;  // whole layer-2 accumulation groups (and an even count)
             c.tc_nch = nch;
             std::vector<float> tp((size_t)F * nch * kTcChunkFloats, 0.f);
             for (int f = 0; f < F; ++f)
@@ -377,6 +410,31 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                     }
                 }
             if (int rc = upload(h, tp, &c.tcpack)) return rc;
+        }
+        // hybrid kernel operands (hy_kernel.cuh): per 64-hidden group [W1 hidden-pair rows | W2 hi tiles | W2 lo tiles]
+        c.hy_ngrp = 0;
+        c.hypack = nullptr;
+        if (hy_has(d, K)) {
+            const int per = kHyGroup * kHyChunk;
+            const int ngrp = (H + per - 1) / per;
+            const int slot = hy_slot_floats(d), w1f = hy_w1_floats(d);
+            c.hy_ngrp = ngrp;
+            std::vector<float> hp((size_t)F * ngrp * slot, 0.f);
+            for (int f = 0; f < F; ++f)
+                for (int j = 0; j < H; ++j) {
+                    float* gp = &hp[((size_t)f * ngrp + j / per) * slot];
+                    const int jj = j % per, ch = jj / kHyChunk, n = jj % kHyChunk;
+                    // chunk ch: 4 hidden pairs, pair row = [b, b', w0, w0', ..., w(d-1), w(d-1)']
+                    float* wr = gp + ch * kHyChunk * (d + 1) + (n / 2) * 2 * (d + 1) + (n & 1);
+                    wr[0] = h->b1[(size_t)f * H + j];
+                    for (int i = 0; i < d; ++i) wr[2 + 2 * i] = h->W1[((size_t)f * d + i) * H + j];
+                    for (int o = 0; o < K; ++o) {
+                        const float w = h->W2[((size_t)f * H + j) * K + o];
+                        tf32_split(w, &gp[w1f + ch * 128 + tc_b_index(kTcN2, o, n)],
+                                   &gp[w1f + kHyB2Floats + ch * 128 + tc_b_index(kTcN2, o, n)]);
+                    }
+                }
+            if (int rc = upload(h, hp, &c.hypack)) return rc;
         }
     } else {
         c.Ntr = h->Ntr;
@@ -402,6 +460,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
     // ---- observations + systematics ----
     h->fused_supported = false;
     h->tc_supported = false;
+    h->hy_supported = false;
     if (h->have_obs) {
         const int G = h->G;
         const int nobs = h->g_off[G];
@@ -464,6 +523,8 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                              fused_smem_bytes(d, K, T, c.S, nobs) <= 227 * 1024;
         h->tc_supported = (h->kind == 0) && direct && K == 10 && c.tc_nch > 0 &&
                           tc_smem_bytes(K, T, c.S, nobs) <= 227 * 1024;
+        h->hy_supported = (h->kind == 0) && direct && hy_has(d, K) && c.hy_ngrp > 0 &&
+                          hy_smem_bytes(d, K, T, c.S, nobs) <= 227 * 1024;
     }
     h->dirty = false;
     return NMMA_B200_OK;
@@ -690,11 +751,15 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused kernel unavailable for this configuration (GP path, averaged filters, or d/K not instantiated)");
     if (path == 3 && !h->tc_supported)
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "tensor-core kernel unavailable for this configuration (GP path, averaged filters, d > 7 or n_coeff != 10)");
+    if (path == 4 && !h->hy_supported)
+        return fail(h, NMMA_B200_ERR_UNSUPPORTED, "hybrid kernel unavailable for this configuration (GP path, averaged filters, d not in {3,4,7} or n_coeff != 10)");
     if (path == 0) {
-        if (h->tc_supported && N >= h->opt_tc_min) path = 3;
+        if (h->hy_supported && N >= h->opt_hy_min) path = 4;
+        else if (h->tc_supported && N >= h->opt_tc_min) path = 3;
         else path = (h->fused_supported && N >= h->opt_fused_min) ? 1 : 2;
     }
     h->last_path = path;
+    if (path == 4) return launch_hy(h, points_dev, N, out_dev, st);
     if (path == 3) return launch_tc(h, points_dev, N, out_dev, st);
     if (path == 1) return launch_fused(h, points_dev, N, out_dev, st);
     const size_t FK = (size_t)h->F * h->K;
@@ -798,9 +863,10 @@ int nmma_b200_mags(nmma_b200_t* h, const double* points_dev, int64_t N, int appa
 int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     if (!h || !key) return NMMA_B200_ERR_ARG;
     const std::string k(key);
-    if (k == "path") { if (value < 0 || value > 3) return fail(h, NMMA_B200_ERR_ARG, "path must be 0, 1, 2 or 3"); h->opt_path = (int)value; }
+    if (k == "path") { if (value < 0 || value > 4) return fail(h, NMMA_B200_ERR_ARG, "path must be 0 .. 4"); h->opt_path = (int)value; }
     else if (k == "fused_min_points") h->opt_fused_min = value;
     else if (k == "tc_min_points") h->opt_tc_min = value;
+    else if (k == "hy_min_points") h->opt_hy_min = value;
     else if (k == "max_ctas") h->opt_max_ctas = (int)value;
     else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }
     else if (k == "no_fast_backend") h->opt_no_fast = value ? 1 : 0;
@@ -817,6 +883,7 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
     else if (k == "sm_count") *value = h->sm_count;
     else if (k == "ctas_per_sm") *value = h->last_ctas_per_sm;
     else if (k == "fused_supported") { if (int rc = finalize(h, true)) return rc; *value = h->fused_supported ? 1 : 0; }
+    else if (k == "hy_supported") { if (int rc = finalize(h, true)) return rc; *value = h->hy_supported ? 1 : 0; }
     else if (k == "tc_supported") { if (int rc = finalize(h, true)) return rc; *value = h->tc_supported ? 1 : 0; }
     else if (k == "algorithmic_flop_per_eval") {
         // F * [2 H (d + K) + 2 T K] (MLP) or Ntr*3d + F*K*Ntr*8 + F*2*T*K (GP)

@@ -5,8 +5,12 @@
 // (profiles/r01_tc_numerics.txt); with a = a_hi + a_lo, b = b_hi + b_lo (hi = top 19 bits, which is exactly what the
 // tensor core reads from an fp32 operand of kind::tf32) the three products a_hi*b_hi + a_lo*b_hi + a_hi*b_lo carry
 // ~2^-21 relative error, the same order as fp32 FFMA.  The tensor core adds into its fp32 accumulator with
-// round-toward-zero (profiles/r01_tc_probe.txt), so accumulation chains are kept to one 32-hidden chunk (12 MMAs)
-// and the chunk partials are summed by the CUDA cores with round-to-nearest adds.
+// round-toward-zero (profiles/r01_tc_probe.txt), so the large layer-2 products h_hi*W_hi accumulate in chains of 16
+// MMAs (one 128-hidden group) whose partials the CUDA cores sum with round-to-nearest adds; the two cross terms are
+// 2^-11 smaller and accumulate over the whole filter in a separate accumulator, where the truncation bias is below
+// 2e-8 relative.  Reading a partial per group instead of per chunk matters: the kernel is bound by TMEM read
+// bandwidth (tcgen05.ld, 64 B/clk/SM; profiles/r01_fused_tc_v2_summary.json), and the layer-1 accumulators alone
+// are 4 B per hidden unit and point.
 //
 // Work decomposition (one persistent CTA per SM, 20 warps, two 128-point tiles in flight):
 //   warps 0-3 / 4-7    activation warps of tile 0 / 1: thread = one parameter point = one TMEM lane.  Per filter they
@@ -41,7 +45,9 @@ constexpr int kTcN2 = 16;                    // layer-2 MMA N (n_coeff padded)
 constexpr uint32_t kColD1 = 0;               // 2 x 32  layer-1 accumulators
 constexpr uint32_t kColA2H = 64;             // 2 x 32  relu(h) (the tensor core reads its top 19 bits = h_hi)
 constexpr uint32_t kColA2L = 128;            // 2 x 32  h_lo
-constexpr uint32_t kColD2 = 192;             // 2 x 16  layer-2 chunk partials
+constexpr uint32_t kColD2 = 192;             // 2 x 16  layer-2 h_hi*W_hi partials, double buffered by 4-chunk group
+constexpr uint32_t kColD2X = 240;            // 16      layer-2 cross terms h_lo*W_hi + h_hi*W_lo of the whole filter
+constexpr int kTcGroup = 4;                  // chunks per layer-2 accumulation chain
 constexpr uint32_t kColA1H = 224;            // 8       [x_hi, 1, 0..]
 constexpr uint32_t kColA1L = 232;            // 8       [x_lo, 0, 0..]
 
@@ -255,14 +261,16 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                         lo[j] = __float_as_uint(h - hh);
                     }
                     if (c >= 2) {
-                        // L2 of chunk c-2 done: its A2 buffer is free and its partial sits in D2[b]
+                        // L2 of chunk c-2 done: its A2 buffer is free; if it closed a group, the partial is complete
                         mbar_wait(&bars->a2_free[t][b], (u - 1) & 1);
                         tc_fence_after();
-                        uint32_t part[16];
-                        tmem_ld16(tbase + kColD2 + 16 * b, part);
-                        tmem_wait_ld();
+                        if (((c - 2) & (kTcGroup - 1)) == kTcGroup - 1) {
+                            uint32_t part[16];
+                            tmem_ld16(tbase + kColD2 + 16 * (((c - 2) / kTcGroup) & 1), part);
+                            tmem_wait_ld();
 #pragma unroll
-                        for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
+                            for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
+                        }
                     }
                     tmem_st32(tbase + kColA2H + 32 * b, v);
                     tmem_st32(tbase + kColA2L + 32 * b, lo);
@@ -271,16 +279,17 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->a2_full[t][b]);
                 }
-                // drain the last two partials
+                // drain: the last group's partial and the cross terms (NCH is a multiple of the group size)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    mbar_wait(&bars->a2_free[t][b], (ubase + half - 1) & 1);
-                    tc_fence_after();
-                    uint32_t part[16];
-                    tmem_ld16(tbase + kColD2 + 16 * b, part);
+                for (int b = 0; b < 2; ++b) mbar_wait(&bars->a2_free[t][b], (ubase + half - 1) & 1);
+                tc_fence_after();
+                {
+                    uint32_t part[16], cr[16];
+                    tmem_ld16(tbase + kColD2 + 16 * (((NCH - 1) / kTcGroup) & 1), part);
+                    tmem_ld16(tbase + kColD2X, cr);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
+                    for (int k = 0; k < K; ++k) acc[k] = (acc[k] + __uint_as_float(part[k])) + __uint_as_float(cr[k]);
                 }
                 tc_fence_before();
                 // ---- hand the coefficients (+ b2 in fp32, Keras Dense) to the back-end warps ----
@@ -337,12 +346,15 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     mbar_wait(&bars->a2_full[t][b], (ubase + ((uint32_t)c >> 1)) & 1);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t d2 = tb + kColD2 + 16 * b, ah = tb + kColA2H + 32 * b, al = tb + kColA2L + 32 * b;
+                        const int cc = c + b;
+                        const uint32_t d2 = tb + kColD2 + 16 * ((cc / kTcGroup) & 1), dx = tb + kColD2X;
+                        const uint32_t ah = tb + kColA2H + 32 * b, al = tb + kColA2L + 32 * b;
+                        const uint32_t gfirst = (cc & (kTcGroup - 1)) == 0 ? 0u : 1u, ffirst = cc == 0 ? 0u : 1u;
 #pragma unroll
                         for (int s = 0; s < 4; ++s) {
-                            mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : 0u);
-                            mma_tf32_ts(d2, al + 8 * s, lo2 + s * 32, hi2, id2, 1u);
-                            mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32 + (2048 >> 4), hi2, id2, 1u);
+                            mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : gfirst);
+                            mma_tf32_ts(dx, al + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : ffirst);
+                            mma_tf32_ts(dx, ah + 8 * s, lo2 + s * 32 + (2048 >> 4), hi2, id2, 1u);
                         }
                         tc_commit(&bars->a2_free[t][b]);
                         tc_commit(&bars->w_free[s2]);
