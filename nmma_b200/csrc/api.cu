@@ -1,7 +1,6 @@
 // C-ABI implementation (include/nmma_b200.h): handle, one-time staging of the
 // surrogate / observation tables into device buffers, and kernel dispatch.
-#include "../../include/nmma_b200.h"
-
+#define NMMA_TWO_STAGE_TU 1  // this translation unit owns the non-template two-stage kernels
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -11,7 +10,8 @@
 #include <string>
 #include <vector>
 
-#include "hy_kernel.cuh"
+#include "handle.h"
+#include "hy_kernel.cuh"  // layout constants of the throughput kernels (weight packs are built here)
 
 using namespace nmma;
 
@@ -21,65 +21,7 @@ constexpr int kVersion = 100;  // 0.1.0
 constexpr long long kTwoStageChunk = 1 << 18;  // points per coefficient-scratch chunk
 }  // namespace
 
-struct nmma_b200_handle {
-    int device = 0;
-    int sm_count = 0;
-    std::string err;
-    // ---- host copies of the configuration ----
-    int F = 0, d = 0, K = 0, T = 0;
-    std::vector<double> tt, pmin, pmax, VA, mins, maxs;
-    bool have_svd = false;
-    int kind = -1;  // 0 mlp, 1 gp
-    int H = 0, Kout = 0;
-    std::vector<float> W1, b1, W2, b2;
-    int Ntr = 0;
-    std::vector<double> gpX, gpAlpha, gpC2, gpRa, gpRl, gpYm, gpYs;
-    std::vector<double> samp;  // empty: default to tt[0]
-    int P = 0;
-    bool have_layout = false;
-    std::vector<ParamSrc> xsrc;
-    ParamSrc dl{-1, 0, 1e-5}, ts{-1, 0, 0.0}, zsrc{-1, 0, 0.0};
-    int zmode = 0;
-    std::vector<double> zd, zz;
-    int G = 0;
-    bool have_obs = false;
-    std::vector<int> g_nh, g_h, g_off;
-    std::vector<double> o_t, o_m, o_s, g_lim;
-    bool have_sys = false;
-    std::vector<int> sy_mode, sy_nn, sy_off;
-    std::vector<double> sy_budget, sy_t;
-    std::vector<ParamSrc> sy_src;
-    // ---- device state ----
-    bool dirty = true;
-    std::vector<void*> dev_allocs;
-    DevCfg cfg{};
-    bool fused_supported = false;
-    bool tc_supported = false;
-    bool hy_supported = false;
-    double* coeff_scratch = nullptr;
-    size_t coeff_cap = 0;
-    double* stage_in_dev = nullptr;
-    double* stage_out_dev = nullptr;
-    double* stage_in_host = nullptr;
-    double* stage_out_host = nullptr;
-    size_t stage_cap_in = 0, stage_cap_out = 0;
-    cudaStream_t own_stream = nullptr;
-    // ---- knobs / counters ----
-    int opt_path = 0;
-    long long opt_fused_min = 2048;
-    long long opt_tc_min = 32768;     // tensor-core path from one wave of 148 CTAs x 256 points up (set_option "tc_min_points")
-    long long opt_hy_min = 32768;     // hybrid (FFMA layer 1 + tcgen05 layer 2) kernel: preferred over the TC kernel
-    int opt_max_ctas = 0;
-    int opt_no_fast = 0;
-    int last_ctas_per_sm = 0;
-    int opt_pt = 0;
-    long long launches = 0;
-    int last_path = 0;
-};
-
-namespace {
-
-int fail(nmma_b200_t* h, int code, const char* fmt, ...) {
+int nmma::fail(nmma_b200_t* h, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -89,12 +31,7 @@ int fail(nmma_b200_t* h, int code, const char* fmt, ...) {
     return code;
 }
 
-#define CU(call)                                                                          \
-    do {                                                                                  \
-        cudaError_t e_ = (call);                                                          \
-        if (e_ != cudaSuccess)                                                            \
-            return fail(h, NMMA_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
-    } while (0)
+namespace {
 
 bool all_finite(const double* p, size_t n) {
     for (size_t i = 0; i < n; ++i)
@@ -125,116 +62,6 @@ int check_src(nmma_b200_t* h, const ParamSrc& s, const char* what) {
 }
 
 ParamSrc to_src(const nmma_b200_param_src& s) { return ParamSrc{s.col, s.transform, s.value}; }
-
-template <int D, int PT, bool FAST>
-int launch_fused_dk(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
-    constexpr int K = 10;
-    auto kern = fused_mlp_logl_kernel<D, K, PT, FAST>;
-    const size_t smem = fused_smem_bytes(D, K, h->T, h->cfg.S, h->cfg.nobs);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem));
-    if (per_sm < 1) return fail(h, NMMA_B200_ERR_CUDA, "fused kernel does not fit on an SM (smem %zu B)", smem);
-    const long long tile = (long long)kFusedThreads * PT;
-    const long long ntiles = (N + tile - 1) / tile;
-    long long grid = (long long)h->sm_count * per_sm;
-    if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
-    grid = std::max<long long>(1, std::min(grid, ntiles));
-    kern<<<(unsigned)grid, kFusedThreads, smem, st>>>(h->cfg, pts, N, out);
-    CU(cudaGetLastError());
-    h->launches += 1;
-    h->last_ctas_per_sm = per_sm;
-    return NMMA_B200_OK;
-}
-
-template <int D, bool FAST>
-int launch_fused_df(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
-    // points per thread: as many as keep every SM busy (a weight fetched from shared memory is
-    // reused PT times; PT = 4 makes the kernel FMA-bound instead of LDS-bound)
-    int pt = h->opt_pt;
-    const long long per_wave = (long long)h->sm_count * kFusedThreads;
-    // measured on B200 (profiles/): PT = 2 at two CTAs per SM beats PT = 4 at one CTA per SM
-    if (pt == 0) pt = (N >= 2 * per_wave) ? 2 : 1;
-    if (pt == 1) return launch_fused_dk<D, 1, FAST>(h, pts, N, out, st);
-    if (pt == 2) return launch_fused_dk<D, 2, FAST>(h, pts, N, out, st);
-    return launch_fused_dk<D, 4, FAST>(h, pts, N, out, st);
-}
-
-template <int D>
-int launch_fused_d(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
-    const bool fast = h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
-    return fast ? launch_fused_df<D, true>(h, pts, N, out, st) : launch_fused_df<D, false>(h, pts, N, out, st);
-}
-
-int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
-    switch (h->d) {
-#ifndef NMMA_DEV_BUILD  // development builds instantiate d = 4 only (compile time)
-        case 2: return launch_fused_d<2>(h, pts, N, out, st);
-        case 3: return launch_fused_d<3>(h, pts, N, out, st);
-        case 5: return launch_fused_d<5>(h, pts, N, out, st);
-        case 6: return launch_fused_d<6>(h, pts, N, out, st);
-        case 7: return launch_fused_d<7>(h, pts, N, out, st);
-#endif
-        case 4: return launch_fused_d<4>(h, pts, N, out, st);
-        default: return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused kernel not instantiated for d=%d", h->d);
-    }
-}
-
-bool fused_has(int d, int K) { return d >= 2 && d <= 7 && K == 10; }
-
-template <bool FAST>
-int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
-    constexpr int K = 10;
-    auto kern = fused_tc_logl_kernel<K, FAST>;
-    const size_t smem = tc_smem_bytes(K, h->T, h->cfg.S, h->cfg.nobs);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long super = (long long)kTcTile * kTcTiles;
-    const long long nsuper = (N + super - 1) / super;
-    long long grid = h->sm_count;  // one CTA per SM: each CTA owns all 512 TMEM columns of its SM
-    if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
-    grid = std::max<long long>(1, std::min(grid, nsuper));
-    kern<<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, out);
-    CU(cudaGetLastError());
-    h->launches += 1;
-    h->last_ctas_per_sm = 1;
-    return NMMA_B200_OK;
-}
-
-int launch_tc(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
-    const bool fast = h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
-    return fast ? launch_tc_f<true>(h, pts, N, out, st) : launch_tc_f<false>(h, pts, N, out, st);
-}
-
-template <int D, bool FAST>
-int launch_hy_df(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
-    constexpr int K = 10;
-    auto kern = fused_hy_logl_kernel<D, K, FAST>;
-    const size_t smem = hy_smem_bytes(D, K, h->T, h->cfg.S, h->cfg.nobs);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long nsuper = (N + kHySuper - 1) / kHySuper;
-    long long grid = h->sm_count;  // one CTA per SM: each CTA owns all 512 TMEM columns of its SM
-    if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
-    grid = std::max<long long>(1, std::min(grid, nsuper));
-    kern<<<(unsigned)grid, kHyThreads, smem, st>>>(h->cfg, pts, N, out);
-    CU(cudaGetLastError());
-    h->launches += 1;
-    h->last_ctas_per_sm = 1;
-    return NMMA_B200_OK;
-}
-
-bool hy_has(int d, int K) { return (d == 3 || d == 4 || d == 7) && K == 10; }
-
-int launch_hy(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
-    const bool fast = h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
-    switch (h->d) {
-#ifndef NMMA_DEV_BUILD
-        case 3: return fast ? launch_hy_df<3, true>(h, pts, N, out, st) : launch_hy_df<3, false>(h, pts, N, out, st);
-        case 7: return fast ? launch_hy_df<7, true>(h, pts, N, out, st) : launch_hy_df<7, false>(h, pts, N, out, st);
-#endif
-        case 4: return fast ? launch_hy_df<4, true>(h, pts, N, out, st) : launch_hy_df<4, false>(h, pts, N, out, st);
-        default: return fail(h, NMMA_B200_ERR_UNSUPPORTED, "hybrid kernel not instantiated for d=%d", h->d);
-    }
-}
 
 // hi = the 19 bits kind::tf32 reads, lo = remainder (exact in fp32; the tensor core truncates it again)
 inline void tf32_split(float w, float* hi, float* lo) {
@@ -754,7 +581,7 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
     if (path == 4 && !h->hy_supported)
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "hybrid kernel unavailable for this configuration (GP path, averaged filters, d not in {3,4,7} or n_coeff != 10)");
     if (path == 0) {
-        if (h->hy_supported && N >= h->opt_hy_min) path = 4;
+        if (h->hy_supported && h->opt_hy_min >= 0 && N >= h->opt_hy_min) path = 4;
         else if (h->tc_supported && N >= h->opt_tc_min) path = 3;
         else path = (h->fused_supported && N >= h->opt_fused_min) ? 1 : 2;
     }

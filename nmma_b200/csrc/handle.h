@@ -1,0 +1,87 @@
+// Host-side state of one engine handle and the launcher entry points shared by the translation units of
+// libnmma_b200.so (api.cu: C ABI, tables, two-stage kernels; launch_fused.cu / launch_tc.cu / launch_hy.cu: one
+// throughput kernel family each, so that they compile in parallel).
+#pragma once
+#include "../../include/nmma_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "backend.cuh"
+
+struct nmma_b200_handle {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    // ---- host copies of the configuration ----
+    int F = 0, d = 0, K = 0, T = 0;
+    std::vector<double> tt, pmin, pmax, VA, mins, maxs;
+    bool have_svd = false;
+    int kind = -1;  // 0 mlp, 1 gp
+    int H = 0, Kout = 0;
+    std::vector<float> W1, b1, W2, b2;
+    int Ntr = 0;
+    std::vector<double> gpX, gpAlpha, gpC2, gpRa, gpRl, gpYm, gpYs;
+    std::vector<double> samp;  // empty: default to tt[0]
+    int P = 0;
+    bool have_layout = false;
+    std::vector<nmma::ParamSrc> xsrc;
+    nmma::ParamSrc dl{-1, 0, 1e-5}, ts{-1, 0, 0.0}, zsrc{-1, 0, 0.0};
+    int zmode = 0;
+    std::vector<double> zd, zz;
+    int G = 0;
+    bool have_obs = false;
+    std::vector<int> g_nh, g_h, g_off;
+    std::vector<double> o_t, o_m, o_s, g_lim;
+    bool have_sys = false;
+    std::vector<int> sy_mode, sy_nn, sy_off;
+    std::vector<double> sy_budget, sy_t;
+    std::vector<nmma::ParamSrc> sy_src;
+    // ---- device state ----
+    bool dirty = true;
+    std::vector<void*> dev_allocs;
+    nmma::DevCfg cfg{};
+    bool fused_supported = false;
+    bool tc_supported = false;
+    bool hy_supported = false;
+    double* coeff_scratch = nullptr;
+    size_t coeff_cap = 0;
+    double* stage_in_dev = nullptr;
+    double* stage_out_dev = nullptr;
+    double* stage_in_host = nullptr;
+    double* stage_out_host = nullptr;
+    size_t stage_cap_in = 0, stage_cap_out = 0;
+    cudaStream_t own_stream = nullptr;
+    // ---- knobs / counters ----
+    int opt_path = 0;
+    long long opt_fused_min = 2048;
+    long long opt_tc_min = 32768;     // tensor-core path from one wave of 148 CTAs x 256 points up (set_option "tc_min_points")
+    long long opt_hy_min = -1;        // hybrid (FFMA layer 1 + tcgen05 layer 2) kernel: opt-in (slower than the TC kernel); < 0 = never automatic
+    int opt_max_ctas = 0;
+    int opt_no_fast = 0;
+    int last_ctas_per_sm = 0;
+    int opt_pt = 0;
+    long long launches = 0;
+    int last_path = 0;
+};
+
+namespace nmma {
+// records the message on the handle (or for a failed create when h == NULL) and returns `code`
+int fail(nmma_b200_t* h, int code, const char* fmt, ...);
+
+// throughput launchers; *_has: is the kernel instantiated for this (d, n_coeff)?
+int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
+bool fused_has(int d, int K);
+int launch_tc(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
+int launch_hy(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
+bool hy_has(int d, int K);
+}  // namespace nmma
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return nmma::fail(h, NMMA_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)

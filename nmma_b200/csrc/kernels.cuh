@@ -15,6 +15,7 @@
 
 namespace nmma {
 
+#ifdef NMMA_TWO_STAGE_TU  // the non-template two-stage kernels are compiled into api.cu only
 // ---------------------------------------------------------------------------------------------
 // Front end (MLP, latency mapping)
 // ---------------------------------------------------------------------------------------------
@@ -232,6 +233,8 @@ backend_mags_kernel(const DevCfg cfg, const double* __restrict__ pts, const doub
         if (tobs != nullptr && f == 0) tobs[n * cfg.S + s] = tobs_at(cfg, s, ps.z1, ps.ts);
     }
 }
+#endif  // NMMA_TWO_STAGE_TU
+
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP)
@@ -598,11 +601,13 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(int iters, float seed, f
     if (s == 123.456f) sink[0] = s;
 }
 
+#ifdef NMMA_TWO_STAGE_TU
 // Diagnostic: elementwise obs_term (parity of the SciPy edge semantics).
 __global__ void obs_terms_kernel(int n, const double* m, const double* mu, const double* so, const double* ss,
                                  const double* lim, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = obs_term(m[i], mu[i], so[i], ss[i], lim[i]);
 }
+#endif  // NMMA_TWO_STAGE_TU
 
 }  // namespace nmma
