@@ -275,8 +275,7 @@ def gpu_arm(args):
         if world == 1:
             lik.log_likelihood_batch(hb.numpy(), cols, out=out_host.numpy())
         else:
-            d = hb.to(dev, non_blocking=True)
-            eng.logl_device(d, out=out_local)
+            eng.logl_host(hb.numpy(), out=out_local)       # pipelined H2D + kernels, result stays on the device
             dist.all_gather_into_tensor(out_all, out_local)
             if rank == 0:
                 out_host.copy_(out_all, non_blocking=True)

@@ -144,7 +144,10 @@ int nmma_b200_set_systematics(nmma_b200_t* h, int G, const int32_t* mode, const 
 int nmma_b200_logl(nmma_b200_t* h, const double* points_dev /* N*P */, int64_t N,
                    double* out_dev /* N */, void* stream);
 /* Same through HOST buffers: pinned staging, H2D, kernels, D2H, synchronised on return.
- * This is the call an unmodified one-point-at-a-time sampler ends up in. */
+ * This is the call an unmodified one-point-at-a-time sampler ends up in.  Large batches
+ * are cut into row blocks (option "pipeline_blocks", default 6) whose copies overlap the
+ * kernels of their neighbours on separate streams.  out_host may also be a DEVICE
+ * pointer: the result then stays on the GPU (the sharded path gathers it with NCCL). */
 int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host);
 /* SVDLightCurveModel.generate_lightcurve (apparent == 0, nmma/em/model.py:707-728:
  * absolute mags on the sample grid, +inf outside the training time range) or
@@ -157,9 +160,64 @@ int nmma_b200_mags(nmma_b200_t* h, const double* points_dev, int64_t N, int appa
 int nmma_b200_coeffs(nmma_b200_t* h, const double* points_dev, int64_t N,
                      double* coeffs_dev, void* stream);
 
+/* ---- priors on the device ------------------------
+ * Replaces bilby's PriorDict.rescale / PriorDict.sample for the sampled columns of
+ * points[N,P] (the reference builds the dict in nmma/em/prior.py:221-244 from
+ * priors/*.prior and calls bilby.core.prior.PriorDict.rescale once per sampler
+ * point; em_syserr* entries come from nmma/em/systematics.py:57-113).  Each column
+ * is one analytic bilby prior, restated from bilby.core.prior.analytical (bilby is
+ * a third-party dependency absent offline; floors only in pyproject.toml:30-53):
+ *   UNIFORM      min + u (max - min)                                   par = min, max
+ *   DELTA        peak                                                  par = peak
+ *   SINE         arccos(cos(min) - u (cos(min) - cos(max)))            par = min, max
+ *   COSINE       arcsin(u (sin(max) - sin(min)) + sin(min))            par = min, max
+ *   GAUSSIAN     mu + erfinv(2u - 1) sqrt(2) sigma                     par = mu, sigma
+ *   TRUNC_GAUSS  erfinv(2 u norm + erf((min-mu)/(sqrt2 sigma))) sqrt(2) sigma + mu
+ *                                                                      par = mu, sigma, min, max
+ *   POWERLAW     (min^(1+a) + u (max^(1+a) - min^(1+a)))^(1/(1+a)); a == -1 (LogUniform):
+ *                min exp(u log(max/min))                               par = alpha, min, max
+ *   TRIANGULAR   inverse CDF of the triangular density                 par = mode, min, max
+ *   INTERPED     np.interp(u, cdf, grid) of a tabulated density (the Ebv prior,
+ *                nmma/em/prior.py:209-216)                             table = cdf[n], grid[n]
+ */
+enum {
+    NMMA_B200_PR_UNIFORM = 0,
+    NMMA_B200_PR_DELTA = 1,
+    NMMA_B200_PR_SINE = 2,
+    NMMA_B200_PR_COSINE = 3,
+    NMMA_B200_PR_GAUSSIAN = 4,
+    NMMA_B200_PR_TRUNC_GAUSS = 5,
+    NMMA_B200_PR_POWERLAW = 6,
+    NMMA_B200_PR_TRIANGULAR = 7,
+    NMMA_B200_PR_INTERPED = 8
+};
+#define NMMA_B200_MAX_P 32
+/* kind[P], par[P*4]; tab_offset[P+1] indexes tab_cdf/tab_grid (equal entries for
+ * non-INTERPED columns; all three may be NULL when no column is INTERPED).
+ * P must equal the P of nmma_b200_set_param_layout when both are set. */
+int nmma_b200_set_priors(nmma_b200_t* h, int P, const int32_t* kind, const double* par /* P*4 */,
+                         const int32_t* tab_offset /* P+1 */, const double* tab_cdf, const double* tab_grid);
+/* PriorDict.rescale for N points: unit_dev[N,P] in [0,1] -> points_dev[N,P] (may alias). */
+int nmma_b200_prior_transform(nmma_b200_t* h, const double* unit_dev, int64_t N, double* points_dev,
+                              void* stream);
+/* PriorDict.sample for N points: counter-based Philox4x32-10 (Salmon et al. 2011, the
+ * generator of cuRAND/torch), key = seed, counter = (global point index, column pair), so
+ * point `first_index + i` is the same on any rank and for any sharding; uniform doubles
+ * from 53 random bits, then the transform above.  unit_dev (N*P, optional) receives the
+ * unit-cube draws. */
+int nmma_b200_prior_sample(nmma_b200_t* h, uint64_t seed, int64_t first_index, int64_t N,
+                           double* points_dev, double* unit_dev, void* stream);
+/* Prior sweep without host traffic (BASELINE.json configs[4]): draws points
+ * first_index .. first_index+N-1 on the device in L2-sized blocks and evaluates
+ * nmma_b200_logl on each; out_dev[N]; points_dev (N*P) may be NULL (blocks are then
+ * drawn into a scratch buffer that never leaves L2). */
+int nmma_b200_logl_sweep(nmma_b200_t* h, uint64_t seed, int64_t first_index, int64_t N,
+                         double* out_dev, double* points_dev, void* stream);
+
 /* ---- knobs / introspection ------------------------------------------- */
 /* keys: "path" (0 auto, 1 fused tile kernel, 2 two-stage front end + back end),
- *       "fused_min_points" (auto threshold), "max_ctas" (0 = one per SM). */
+ *       "fused_min_points" (auto threshold), "max_ctas" (0 = one per SM),
+ *       "pipeline_blocks" (row blocks of the nmma_b200_logl_host copy/compute pipeline, 1 = serial). */
 int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value);
 /* keys: "launches" (kernels launched by this handle so far), "last_path",
  *       "sm_count", "fused_supported", "algorithmic_flop_per_eval". */

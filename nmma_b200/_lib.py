@@ -15,6 +15,9 @@ OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 XF_NONE, XF_RAD2DEG, XF_LOG10, XF_POW10, XF_THETAJN_DEG, XF_COSTHETAJN_DEG = range(6)
 Z_ZERO, Z_PARAM, Z_TABLE = 0, 1, 2
 SYS_BUDGET, SYS_PARAM, SYS_INTERP = 0, 1, 2
+(PR_UNIFORM, PR_DELTA, PR_SINE, PR_COSINE, PR_GAUSSIAN, PR_TRUNC_GAUSS, PR_POWERLAW, PR_TRIANGULAR,
+ PR_INTERPED) = range(9)
+MAX_P = 32
 
 
 class ParamSrc(C.Structure):
@@ -59,6 +62,10 @@ SIGNATURES = {
     "nmma_b200_logl_host": (C.c_int, [_h, _dp, C.c_int64, _dp]),
     "nmma_b200_mags": (C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmma_b200_coeffs": (C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "nmma_b200_set_priors": (C.c_int, [_h, C.c_int, _ip, _dp, _ip, _dp, _dp]),
+    "nmma_b200_prior_transform": (C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "nmma_b200_prior_sample": (C.c_int, [_h, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nmma_b200_logl_sweep": (C.c_int, [_h, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmma_b200_set_option": (C.c_int, [_h, C.c_char_p, C.c_int64]),
     "nmma_b200_get_info": (C.c_int, [_h, C.c_char_p, C.POINTER(C.c_int64)]),
     "nmma_b200_ffma_peak": (C.c_int, [_h, C.c_int, C.c_int, _dp]),

@@ -342,5 +342,35 @@ class PriorDict(OrderedDict):
         u = rng.uniform(0, 1, size=(n, len(keys)))
         return np.stack([np.asarray(self[k].rescale(u[:, i]), float) for i, k in enumerate(keys)], axis=1), keys
 
+    def device_plan(self, keys=None):
+        """``(kinds[P], params[P,4], tables{j: (cdf, grid)})`` for ``nmma_b200_set_priors``: one analytic
+        prior per column of ``points[N,P]`` (``keys`` default: the sampled keys in prior order)."""
+        from .. import _lib as L
+        keys = list(keys) if keys is not None else self.non_fixed_keys
+        kinds, params, tables = [], np.zeros((len(keys), 4)), {}
+        for j, k in enumerate(keys):
+            p = self[k]
+            if is_fixed_prior(p):
+                kinds.append(L.PR_DELTA); params[j, 0] = fixed_value(p)
+            elif isinstance(p, Uniform):
+                kinds.append(L.PR_UNIFORM); params[j, :2] = p.minimum, p.maximum
+            elif isinstance(p, Sine):
+                kinds.append(L.PR_SINE); params[j, :2] = p.minimum, p.maximum
+            elif isinstance(p, Cosine):
+                kinds.append(L.PR_COSINE); params[j, :2] = p.minimum, p.maximum
+            elif isinstance(p, TruncatedGaussian):
+                kinds.append(L.PR_TRUNC_GAUSS); params[j] = p.mu, p.sigma, p.minimum, p.maximum
+            elif isinstance(p, Gaussian):
+                kinds.append(L.PR_GAUSSIAN); params[j, :2] = p.mu, p.sigma
+            elif isinstance(p, PowerLaw):
+                kinds.append(L.PR_POWERLAW); params[j, :3] = p.alpha, p.minimum, p.maximum
+            elif isinstance(p, Triangular):
+                kinds.append(L.PR_TRIANGULAR); params[j, :3] = p.mode, p.minimum, p.maximum
+            elif isinstance(p, Interped):
+                kinds.append(L.PR_INTERPED); tables[j] = (p._cdf, p._grid)
+            else:
+                raise NotImplementedError(f"prior {k} = {p!r} has no device transform")
+        return np.asarray(kinds, np.int32), params, tables
+
     def ln_prob(self, sample):
         return float(np.sum([self[k].ln_prob(sample[k]) for k in sample if k in self and not is_constraint(self[k])]))

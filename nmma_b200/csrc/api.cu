@@ -398,11 +398,17 @@ int nmma_b200_destroy(nmma_b200_t* h) {
     cudaSetDevice(h->device);
     free_dev(h);
     if (h->coeff_scratch) cudaFree(h->coeff_scratch);
+    if (h->pr_dev) cudaFree(h->pr_dev);
+    if (h->pr_tab_dev) cudaFree(h->pr_tab_dev);
+    if (h->sweep_scratch) cudaFree(h->sweep_scratch);
     if (h->stage_in_dev) cudaFree(h->stage_in_dev);
     if (h->stage_out_dev) cudaFree(h->stage_out_dev);
     if (h->stage_in_host) cudaFreeHost(h->stage_in_host);
     if (h->stage_out_host) cudaFreeHost(h->stage_out_host);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_in_stream) cudaStreamDestroy(h->copy_in_stream);
+    if (h->copy_out_stream) cudaStreamDestroy(h->copy_out_stream);
+    for (cudaEvent_t ev : h->pipe_events) cudaEventDestroy(ev);
     delete h;
     return NMMA_B200_OK;
 }
@@ -611,6 +617,11 @@ static bool is_pinned_host(const void* p) {
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
 }
+static bool is_device_mem(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice;
+}
 
 int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host) {
     if (!h) return NMMA_B200_ERR_ARG;
@@ -621,7 +632,9 @@ int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, do
     CU(cudaSetDevice(h->device));
     const size_t nin = (size_t)N * h->P, nout = (size_t)N;
     // page-locked caller buffers are copied directly; pageable ones go through pinned staging
-    const bool in_pinned = is_pinned_host(points_host), out_pinned = is_pinned_host(out_host);
+    // a DEVICE out pointer keeps the result on the GPU (no D2H): the sharded path gathers it with NCCL
+    const bool in_pinned = is_pinned_host(points_host), out_dev = is_device_mem(out_host);
+    const bool out_pinned = out_dev || is_pinned_host(out_host);
     if (nin > h->stage_cap_in) {
         if (h->stage_in_dev) cudaFree(h->stage_in_dev);
         if (h->stage_in_host) cudaFreeHost(h->stage_in_host);
@@ -630,7 +643,7 @@ int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, do
         CU(cudaMallocHost((void**)&h->stage_in_host, nin * sizeof(double)));
         h->stage_cap_in = nin;
     }
-    if (nout > h->stage_cap_out) {
+    if (!out_dev && nout > h->stage_cap_out) {
         if (h->stage_out_dev) cudaFree(h->stage_out_dev);
         if (h->stage_out_host) cudaFreeHost(h->stage_out_host);
         h->stage_out_dev = nullptr; h->stage_out_host = nullptr; h->stage_cap_out = 0;
@@ -638,13 +651,49 @@ int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, do
         CU(cudaMallocHost((void**)&h->stage_out_host, nout * sizeof(double)));
         h->stage_cap_out = nout;
     }
-    const double* src = points_host;
-    if (!in_pinned) { std::memcpy(h->stage_in_host, points_host, nin * sizeof(double)); src = h->stage_in_host; }
     double* dst = out_pinned ? out_host : h->stage_out_host;
-    CU(cudaMemcpyAsync(h->stage_in_dev, src, nin * sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
-    if (int rc = nmma_b200_logl(h, h->stage_in_dev, N, h->stage_out_dev, h->own_stream)) return rc;
-    CU(cudaMemcpyAsync(dst, h->stage_out_dev, nout * sizeof(double), cudaMemcpyDeviceToHost, h->own_stream));
-    CU(cudaStreamSynchronize(h->own_stream));
+    double* res = out_dev ? out_host : h->stage_out_dev;
+    // Copy/compute pipeline: the batch is cut into row blocks (whole waves of the persistent throughput kernels);
+    // block c+1 crosses PCIe (and, for pageable callers, is staged into pinned memory) while block c computes, and
+    // block c-1 returns.  Three streams, one event pair per block; only the first H2D and the last D2H are exposed.
+    long long nblk = 1;
+    const long long wave = (long long)h->sm_count * 256;
+    if (h->opt_pipeline > 1 && N >= 4 * wave) nblk = std::min<long long>(h->opt_pipeline, N / (2 * wave));
+    long long rows = (N + nblk - 1) / nblk;
+    if (nblk > 1) rows = (rows + wave - 1) / wave * wave;
+    nblk = (N + rows - 1) / rows;
+    if (nblk == 1) {
+        const double* src = points_host;
+        if (!in_pinned) { std::memcpy(h->stage_in_host, points_host, nin * sizeof(double)); src = h->stage_in_host; }
+        CU(cudaMemcpyAsync(h->stage_in_dev, src, nin * sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
+        if (int rc = nmma_b200_logl(h, h->stage_in_dev, N, res, h->own_stream)) return rc;
+        if (!out_dev) CU(cudaMemcpyAsync(dst, res, nout * sizeof(double), cudaMemcpyDeviceToHost, h->own_stream));
+        CU(cudaStreamSynchronize(h->own_stream));
+    } else {
+        if (!h->copy_in_stream) CU(cudaStreamCreateWithFlags(&h->copy_in_stream, cudaStreamNonBlocking));
+        if (!h->copy_out_stream) CU(cudaStreamCreateWithFlags(&h->copy_out_stream, cudaStreamNonBlocking));
+        while ((long long)h->pipe_events.size() < 2 * nblk) {
+            cudaEvent_t ev;
+            CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            h->pipe_events.push_back(ev);
+        }
+        for (long long c = 0; c < nblk; ++c) {
+            const long long r0 = c * rows, nr = std::min<long long>(rows, N - r0);
+            const size_t o = (size_t)r0 * h->P, nb = (size_t)nr * h->P * sizeof(double);
+            const double* src = points_host + o;
+            if (!in_pinned) { std::memcpy(h->stage_in_host + o, points_host + o, nb); src = h->stage_in_host + o; }
+            CU(cudaMemcpyAsync(h->stage_in_dev + o, src, nb, cudaMemcpyHostToDevice, h->copy_in_stream));
+            CU(cudaEventRecord(h->pipe_events[2 * c], h->copy_in_stream));
+            CU(cudaStreamWaitEvent(h->own_stream, h->pipe_events[2 * c], 0));
+            if (int rc = nmma_b200_logl(h, h->stage_in_dev + o, nr, res + r0, h->own_stream)) return rc;
+            if (out_dev) continue;
+            CU(cudaEventRecord(h->pipe_events[2 * c + 1], h->own_stream));
+            CU(cudaStreamWaitEvent(h->copy_out_stream, h->pipe_events[2 * c + 1], 0));
+            CU(cudaMemcpyAsync(dst + r0, res + r0, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost,
+                               h->copy_out_stream));
+        }
+        CU(cudaStreamSynchronize(out_dev ? h->own_stream : h->copy_out_stream));
+    }
     if (!out_pinned) std::memcpy(out_host, h->stage_out_host, nout * sizeof(double));
     return NMMA_B200_OK;
 }
@@ -695,6 +744,7 @@ int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     else if (k == "tc_min_points") h->opt_tc_min = value;
     else if (k == "hy_min_points") h->opt_hy_min = value;
     else if (k == "max_ctas") h->opt_max_ctas = (int)value;
+    else if (k == "pipeline_blocks") { if (value < 1 || value > 64) return fail(h, NMMA_B200_ERR_ARG, "pipeline_blocks must be 1..64"); h->opt_pipeline = (int)value; }
     else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }
     else if (k == "no_fast_backend") h->opt_no_fast = value ? 1 : 0;
     else if (k == "points_per_thread") { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, NMMA_B200_ERR_ARG, "points_per_thread must be 0 (auto), 1, 2 or 4"); h->opt_pt = (int)value; }

@@ -11,6 +11,9 @@
 
 #include "backend.cuh"
 
+namespace nmma {
+struct PriorPlan;
+}
 struct nmma_b200_handle {
     int device = 0;
     int sm_count = 0;
@@ -39,6 +42,13 @@ struct nmma_b200_handle {
     std::vector<int> sy_mode, sy_nn, sy_off;
     std::vector<double> sy_budget, sy_t;
     std::vector<nmma::ParamSrc> sy_src;
+    // ---- priors on the device (prior.cu) ----
+    int prP = 0;
+    int pr_tab_total = 0;                   // entries in each half (cdf | grid) of pr_tab_dev
+    nmma::PriorPlan* pr_dev = nullptr;      // device copy of the per-column prior plan
+    double* pr_tab_dev = nullptr;           // INTERPED tables: cdf values then grid values
+    double* sweep_scratch = nullptr;        // L2-sized block of drawn points for nmma_b200_logl_sweep
+    size_t sweep_cap = 0;
     // ---- device state ----
     bool dirty = true;
     std::vector<void*> dev_allocs;
@@ -54,6 +64,9 @@ struct nmma_b200_handle {
     double* stage_out_host = nullptr;
     size_t stage_cap_in = 0, stage_cap_out = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_in_stream = nullptr, copy_out_stream = nullptr;   // nmma_b200_logl_host copy/compute pipeline
+    std::vector<cudaEvent_t> pipe_events;
+    int opt_pipeline = 6;             // row blocks of the host-buffer pipeline (set_option "pipeline_blocks"; 1 = serial)
     // ---- knobs / counters ----
     int opt_path = 0;
     long long opt_fused_min = 2048;

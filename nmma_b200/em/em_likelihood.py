@@ -145,6 +145,11 @@ class MultiFilterTransient:
         eng.set_observations(*plan["obs"])
         eng.set_systematics(*plan["sys"])
         self._always_fail = plan["always_fail"]
+        if hasattr(self.priors, "device_plan"):
+            try:
+                eng.set_priors(*self.priors.device_plan(columns))
+            except (NotImplementedError, KeyError):
+                pass        # a column without a device prior: prior_transform / sweep raise ERR_STATE when used
         self._engine = eng
         self._columns = list(columns)
         return eng
@@ -171,6 +176,23 @@ class MultiFilterTransient:
         if self._always_fail:
             out[:] = SENTINEL
         return out
+
+    def prior_transform_batch(self, unit, columns: Optional[Sequence[str]] = None):
+        """``PriorDict.rescale`` on the device: ``unit[N,P]`` in the unit cube -> CUDA ``points[N,P]``."""
+        return self.engine_for(columns).prior_transform(unit)
+
+    def sample_prior_batch(self, n, seed=0, first_index=0, columns: Optional[Sequence[str]] = None):
+        """``n`` prior draws on the device (counter-based: draw ``first_index + i`` does not depend on sharding)."""
+        return self.engine_for(columns).prior_sample(n, seed, first_index)
+
+    def log_likelihood_sweep(self, n, seed=0, first_index=0, return_points=False,
+                             columns: Optional[Sequence[str]] = None):
+        """log L of ``n`` prior draws with no host traffic; sentinel semantics as ``log_likelihood_batch``."""
+        eng = self.engine_for(columns)
+        res = eng.logl_sweep(n, seed, first_index, return_points)
+        if self._always_fail:
+            (res[0] if return_points else res).fill_(SENTINEL)
+        return res
 
     def log_likelihood(self, parameters):
         """One point, dict in / float out (``nmma/em/em_likelihood.py:186-204``)."""
@@ -225,6 +247,34 @@ class EMTransientLikelihood(NMMALikelihood):
             raise NotImplementedError("Constraint priors are evaluated per point on the host; "
                                       "use log_likelihood(dict) or drop the constraint for batched sweeps")
         return self.sub_model.log_likelihood_batch(points, columns, out=out)
+
+    def prior_transform_batch(self, unit, columns: Optional[Sequence[str]] = None):
+        """Vectorised ``priors.rescale`` on the device (ultranest ``transform`` with ``vectorized=True``)."""
+        return self.sub_model.prior_transform_batch(unit, columns)
+
+    def sample_prior_batch(self, n, seed=0, first_index=0, columns: Optional[Sequence[str]] = None):
+        return self.sub_model.sample_prior_batch(n, seed, first_index, columns)
+
+    def log_likelihood_sweep(self, n, seed=0, first_index=0, return_points=False,
+                             columns: Optional[Sequence[str]] = None):
+        """Prior sweep (BASELINE.json configs[1] and [4]) with the draws made on the device."""
+        if self.constraints:
+            raise NotImplementedError("Constraint priors are evaluated per point on the host")
+        return self.sub_model.log_likelihood_sweep(n, seed, first_index, return_points, columns)
+
+    def vectorized(self, columns: Optional[Sequence[str]] = None):
+        """``(transform, loglike)`` callables for vectorised samplers (ultranest ``ReactiveNestedSampler(
+        param_names, loglike, transform, vectorized=True)``; dynesty ``prior_transform`` on stacked live points):
+        NumPy ``[N,P]`` in, NumPy out, one GPU call each."""
+        cols = list(columns) if columns is not None else self.columns
+
+        def transform(unit):
+            return self.prior_transform_batch(np.atleast_2d(np.asarray(unit, float)), cols).cpu().numpy()
+
+        def loglike(theta):
+            return self.log_likelihood_batch(np.atleast_2d(np.asarray(theta, float)), cols)
+
+        return transform, loglike
 
     @property
     def columns(self):

@@ -192,6 +192,12 @@ class KilonovaEngine:
             raise ValueError(f"points must have shape [N, {self.P}], got {pts.shape}")
         if out is None:
             out = np.empty(pts.shape[0], np.float64)
+        if hasattr(out, "is_cuda"):        # CUDA tensor: the result stays on the device (sharded path, NCCL gather next)
+            import torch
+            assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() == pts.shape[0]
+            self._check(self._lib.nmma_b200_logl_host(self._h, _dptr(pts), pts.shape[0],
+                                                      C.cast(C.c_void_p(out.data_ptr()), C.POINTER(C.c_double))))
+            return out
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == pts.shape[0]
         self._check(self._lib.nmma_b200_logl_host(self._h, _dptr(pts), pts.shape[0], _dptr(out)))
         return out
@@ -225,6 +231,73 @@ class KilonovaEngine:
         out = np.empty(arrs[0].size, np.float64)
         self._check(self._lib.nmma_b200_obs_terms(self._h, out.size, *[_dptr(a) for a in arrs], _dptr(out)))
         return out
+
+    # ---- priors on the device -------------------------------------------------------------
+    def set_priors(self, kinds, params, tables=None):
+        """Stage one analytic prior per column (``PriorDict.device_plan``): ``kinds[P]`` in PR_*,
+        ``params[P,4]``, ``tables[j] = (cdf, grid)`` for PR_INTERPED columns."""
+        kinds = np.ascontiguousarray(kinds, np.int32)
+        par = _f64(params).reshape(len(kinds), 4)
+        P = len(kinds)
+        off = np.zeros(P + 1, np.int32)
+        cdfs, grids = [], []
+        for j in range(P):
+            n = 0
+            if tables and tables.get(j) is not None:
+                cdf, grid = (np.asarray(a, float).ravel() for a in tables[j])
+                assert cdf.shape == grid.shape
+                cdfs.append(cdf); grids.append(grid); n = cdf.size
+            off[j + 1] = off[j] + n
+        if off[-1]:
+            cdf, grid = _f64(np.concatenate(cdfs)), _f64(np.concatenate(grids))
+            self._check(self._lib.nmma_b200_set_priors(self._h, P, _iptr(kinds), _dptr(par), _iptr(off),
+                                                       _dptr(cdf), _dptr(grid)))
+        else:
+            self._check(self._lib.nmma_b200_set_priors(self._h, P, _iptr(kinds), _dptr(par), _iptr(off), None, None))
+        self.prior_P = P
+
+    def prior_transform(self, unit, out=None):
+        """``PriorDict.rescale`` of a CUDA (or NumPy -> copied) ``unit[N,P]``; returns a CUDA tensor."""
+        import torch
+        if isinstance(unit, torch.Tensor):
+            u = unit.to(dtype=torch.float64).contiguous()
+            if not u.is_cuda:
+                raise ValueError("tensor input must live on the GPU; pass a NumPy array for host data")
+        else:
+            u = torch.from_numpy(_f64(unit)).to(f"cuda:{self.device}")
+        if u.ndim != 2 or u.shape[1] != self.prior_P:
+            raise ValueError(f"unit cube must have shape [N, {self.prior_P}], got {tuple(u.shape)}")
+        if out is None:
+            out = torch.empty_like(u)
+        with torch.cuda.device(u.device):
+            self._check(self._lib.nmma_b200_prior_transform(self._h, C.c_void_p(u.data_ptr()), u.shape[0],
+                                                            C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def prior_sample(self, n: int, seed: int = 0, first_index: int = 0, return_unit: bool = False):
+        """``n`` prior draws on the device (Philox4x32-10 keyed by ``seed``, counter = global point index)."""
+        import torch
+        dev = torch.device(f"cuda:{self.device}")
+        pts = torch.empty((int(n), self.prior_P), dtype=torch.float64, device=dev)
+        unit = torch.empty_like(pts) if return_unit else None
+        with torch.cuda.device(dev):
+            self._check(self._lib.nmma_b200_prior_sample(
+                self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), int(first_index), int(n), C.c_void_p(pts.data_ptr()),
+                C.c_void_p(unit.data_ptr()) if unit is not None else None, self._stream()))
+        return (pts, unit) if return_unit else pts
+
+    def logl_sweep(self, n: int, seed: int = 0, first_index: int = 0, return_points: bool = False, out=None):
+        """log L of ``n`` prior draws without host traffic (``nmma_b200_logl_sweep``)."""
+        import torch
+        dev = torch.device(f"cuda:{self.device}")
+        if out is None:
+            out = torch.empty(int(n), dtype=torch.float64, device=dev)
+        pts = torch.empty((int(n), self.prior_P), dtype=torch.float64, device=dev) if return_points else None
+        with torch.cuda.device(dev):
+            self._check(self._lib.nmma_b200_logl_sweep(
+                self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), int(first_index), int(n), C.c_void_p(out.data_ptr()),
+                C.c_void_p(pts.data_ptr()) if pts is not None else None, self._stream()))
+        return (out, pts) if return_points else out
 
     # ---- knobs -------------------------------------------------------------------------
     def set_option(self, key: str, value: int):
