@@ -140,6 +140,17 @@ int finalize(nmma_b200_t* h, bool need_obs) {
     if (int rc = upload(h, h->pmin, &c.pmin)) return rc;
     if (int rc = upload(h, pden, &c.pden)) return rc;
     if (int rc = upload(h, bpack, &c.bpack)) return rc;
+    {   // fp32 row-pair pack of the FAST back end (backend.cuh: DevCfg::bpack32)
+        std::vector<float2> b32((size_t)F * (K + 2) * T);
+        for (int f = 0; f < F; ++f)
+            for (int i = 0; i < K + 2; ++i)
+                for (int j = 0; j < T; ++j) {
+                    const int j1 = std::min(j + 1, T - 1);
+                    b32[((size_t)f * (K + 2) + i) * T + j] =
+                        make_float2((float)bpack[((size_t)f * T + j) * (K + 2) + i], (float)bpack[((size_t)f * T + j1) * (K + 2) + i]);
+                }
+        if (int rc = upload(h, b32, &c.bpack32)) return rc;
+    }
 
     // ---- stage 1 tables: np.interp(sample_times, tt_f, ., left=inf, right=inf) ----
     std::vector<double> samp = h->samp;
@@ -187,6 +198,9 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         for (int s = 0; s < S && uni; ++s)
             if (std::fabs(samp[s] - (samp[0] + s * ds)) > 1e-6 * ds) uni = false;
         if (uni) { c.uniform = 1; c.uni_s0 = samp[0]; c.uni_inv_ds = 1.0 / ds; }
+        // fp32 index guess: |error| <= ~4 ulp(S) + the 1e-6 non-uniformity admitted above; 16x margin, >= 2^-10
+        c.fast_delta = std::max(1.0f / 1024.0f, (float)S * 8e-6f);
+        if (c.fast_delta >= 0.25f) c.uniform = 0;   // grid too long for an fp32 guess: exact path only
     }
     if (int rc = upload(h, samp, &c.samp)) return rc;
     if (int rc = upload(h, s_lo, &c.s_lo)) return rc;
@@ -231,7 +245,9 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                     }
                     const int s = n / 8, kk = n % 8;
                     for (int o = 0; o < K; ++o) {
-                        const float w = h->W2[((size_t)f * H + j) * K + o];
+                        // halved (exact): the activation warps hand over 2 relu(v) = v + |v|, one FADD on the FMA pipe
+                        // instead of an FMNMX on the half-rate ALU pipe; products and sums are bit-identical
+                        const float w = 0.5f * h->W2[((size_t)f * H + j) * K + o];
                         tf32_split(w, &ch[512 + s * 128 + tc_b_index(kTcN2, o, kk)],
                                    &ch[1024 + s * 128 + tc_b_index(kTcN2, o, kk)]);
                     }
@@ -318,6 +334,11 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                 double* rec = &o_pack[(size_t)k * kObsRec];
                 rec[0] = h->o_t[k]; rec[1] = h->o_m[k]; rec[2] = h->o_s[k];
                 rec[3] = sg; rec[4] = 1.0 / sg; rec[5] = o_lsc[k];
+                float* rf = reinterpret_cast<float*>(rec + 6);
+                rf[0] = (float)h->o_t[k]; rf[1] = (float)h->o_m[k]; rf[2] = (float)(1.0 / sg); rf[3] = (float)o_lsc[k];
+                // plain detection: constant budget, no detection limit, finite sigma_obs (fp32 Gaussian term)
+                const int simple = (sy_mode[g] == 0 && h->g_lim[g] == INFINITY && std::isfinite(h->o_s[k])) ? 1 : 0;
+                std::memcpy(rec + 8, &simple, sizeof(int));
             }
         std::vector<int> f_goff(F + 1, 0), f_glist;
         bool direct = true;

@@ -21,6 +21,11 @@ struct DevCfg {
     const double* pmin;   // F*d
     const double* pden;   // F*d   param_maxs - param_mins
     const double* bpack;  // F*T*(K+2): row j = [VA[j,0..K-1], maxs[j]-mins[j], mins[j]]
+    // fp32 copy for the FAST back end (kernels.cuh: fused_filter_logl): F*(K+2)*T float2, entry (i, j) = column i of
+    // rows j and min(j+1, T-1) -- the two grid nodes that bracket an observation come back in one 8-byte load, and
+    // lanes with different j hit different banks.  Same byte count per filter as bpack.
+    const float2* bpack32;
+    float fast_delta;     // FAST back end: |frac(index guess) - {0,1}| below this -> settle the interval in fp64
     // stage 1: tt -> sample grid (np.interp with +inf outside the training range)
     const double* samp;   // S
     const int* s_lo;      // F  first sample node inside [tt[0], tt[-1]]
@@ -76,8 +81,17 @@ struct DevCfg {
 
 struct PointScal {
     double z1, ts, dm, zc;
+    float ga, gb, dmz;  // FAST back end: index guess = fma((float)t, ga, gb) on a uniform grid; dm + zc in fp32
     bool bad;
 };
+
+// FAST back end scalars: detector-frame node j sits at (samp[0] + j ds) z1 + ts  ->  j(t) = (t - ts) / (z1 ds) - samp[0] / ds
+__device__ __forceinline__ void point_fast_fields(const DevCfg& cfg, PointScal& ps) {
+    const double inv = cfg.uni_inv_ds / ps.z1;
+    ps.ga = (float)inv;
+    ps.gb = (float)(-(ps.ts * inv + cfg.uni_s0 * cfg.uni_inv_ds));
+    ps.dmz = (float)(ps.dm + ps.zc);
+}
 
 // em_parameter_setup (nmma/em/model.py:288-303) + redshift_from_dlum (:259-263) +
 // the scalars of gen_detector_lc / combine_detector_data (:374,393).
@@ -92,6 +106,7 @@ __device__ __forceinline__ PointScal point_setup(const DevCfg& cfg, const double
     ps.dm = 5.0 * (5 + log10(dl));
     ps.zc = -2.5 * log10(ps.z1);
     ps.bad = !(isfinite(ps.z1) && isfinite(ps.ts));
+    point_fast_fields(cfg, ps);
     return ps;
 }
 

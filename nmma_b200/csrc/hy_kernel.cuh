@@ -307,6 +307,7 @@ fused_hy_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                         ps.dm = s_ps[(o * 4 + 2) * kHyActThreads + at];
                         ps.zc = s_ps[(o * 4 + 3) * kHyActThreads + at];
                         ps.bad = false;
+                        point_fast_fields(cfg, ps);
                         const long long nn = n0 + (long long)t * kTcTile;
                         const double* row = pts + (nn < N ? nn : 0) * cfg.P;
                         const double v = fused_filter_logl<K, FAST>(cfg, f, cp, ps, row, basis, s_obs, s_samp);
@@ -387,7 +388,7 @@ fused_hy_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             mbar_wait(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&bars->b_full[slot], bbytes);
-                bulk_g2s(s_basis0 + slot * bslot, cfg.bpack + (size_t)f * cfg.T * (K + 2), bbytes, &bars->b_full[slot]);
+                bulk_g2s(s_basis0 + slot * bslot, basis_src<FAST>(cfg, f, K), bbytes, &bars->b_full[slot]);
             }
             __syncwarp();
             const float* src = cfg.hypack + (size_t)f * NG * SLOT;

@@ -264,6 +264,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// Wait of a warp that is not on the critical path (producer, back end): the hardware may keep the thread suspended for
+// up to `hint_ns` before try_wait returns, so an idle warp does not burn issue slots re-polling the barrier.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 100000u) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+    }
+}
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0).
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -288,7 +302,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 constexpr int kFusedThreads = 256;   // 8 warps, all consumers
 constexpr int kHC = 128;             // hidden units per weight chunk (8 KB at 16 floats per unit)
 constexpr int kWStages = 6;          // weight ring depth
-constexpr int kObsRec = 6;           // doubles per staged observation record
+constexpr int kObsRec = 10;          // doubles per staged observation record: t, mag, sigma_obs, sigma, 1/sigma,
+                                     // log(sigma)+C | fp32 (t, mag, 1/sigma, log(sigma)+C) | int simple-detection flag, pad
 
 __host__ __device__ constexpr int fused_rw(int D, int K) { return (D + 1 + K + 3) / 4 * 4; }
 __host__ __device__ inline size_t fused_bslot(int K, int T) {
@@ -307,81 +322,114 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // observation of the observed filters mapped onto f, interpolates to the observation time (np.interp semantics,
 // em_likelihood.py:313-335) and returns the sum of the per-observation terms (em_likelihood.py:224-256).
 // `bp` = basis pack of filter f, `s_obs` = observation records, `s_samp` = sample grid, all in shared memory.
-template <int K, bool FAST>
-__device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, const double (&cp)[K], const PointScal& ps,
+//
+// Precision split of the FAST instantiation (sample grid = uniform training grid).  fp64 issues at a small fraction
+// of the fp32 rate on B200 (profiles/r01_fp64_rate.txt) and the all-fp64 back end was the co-critical resource of the
+// fused kernels (profiles/r01_fused_tc_v3_source_stalls.md), so fp64 is kept where the result is discrete or
+// accumulates and dropped where the north-star tolerance (1e-3 mag) leaves three orders of margin:
+//   * interval index: guess j = floor(fma((float)t, ga, gb)).  The guess is within 5e-5 of the exact index
+//     coordinate (fp32 rounding at index <= a few hundred, grid uniform to 1e-6 ds), so when its fractional part is
+//     farther than cfg.fast_delta from 0 and 1 the interval is decided; otherwise (and at the range ends) the exact
+//     fp64 comparisons np.interp's bisection would make decide it -> indices and in/out-of-range masks bit-exact.
+//   * detector-frame node time t_j = fl(fl(samp[j] z1) + ts) and t - t_j in fp64 (cancellation), weight in fp32.
+//   * SVD reconstruction of the two bracketing rows, de-normalisation, interpolation, distance modulus: fp32 FFMA
+//     from the float2 row-pair pack (cfg.bpack32): ~1e-5 mag, the size of the fp32 MLP's own rounding noise.
+//   * Gaussian term of a plain detection in fp32, summed over observations and filters in fp64; upper limits,
+//     finite detection limits and sampled systematics go through the fp64 obs_term with the same mu.
+template <int K, bool FAST, typename CT>
+__device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, const CT (&cp)[K], const PointScal& ps,
                                                     const double* __restrict__ row, const double* __restrict__ bp,
                                                     const double* __restrict__ s_obs, const double* __restrict__ s_samp) {
     const int lo = cfg.s_lo[f], hi = cfg.s_hi[f];
     const double z1 = ps.z1, tsh = ps.ts;
-    const double inv_z1 = 1.0 / z1;
-    const double tlo = __dadd_rn(__dmul_rn(s_samp[lo], z1), tsh);
-    const double thi = __dadd_rn(__dmul_rn(s_samp[hi], z1), tsh);
     double lsum = 0.0;
-    for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
-        const int g = cfg.f_glist[gi];
-        const double lim = cfg.g_lim[g];
-        const int mode = cfg.sy_mode[g];
-        const int k1 = cfg.g_off[g + 1];
-        for (int k = cfg.g_off[g]; k < k1; ++k) {
-            const double* rec = s_obs + k * kObsRec;  // t, mag, sigma_obs, sigma, 1/sigma, log(sigma)+C
-            const double t = rec[0], m = rec[1], so = rec[2];
-            double mu;
-            if constexpr (FAST) {
-                if (t < tlo || t > thi) {
-                    mu = CUDART_INF;  // np.interp left = right = +inf
-                } else {
-                    // interval search: O(1) guess from the inverse map, settled by the exact
-                    // (mul, add) comparisons np.interp's bisection would make
-                    const double gq = (__dsub_rn(t, tsh) * inv_z1 - cfg.uni_s0) * cfg.uni_inv_ds;
-                    int j = (gq >= (double)hi) ? hi : ((gq <= (double)lo) ? lo : (int)gq);
-                    double tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh);
-                    double tj1 = (j < hi) ? __dadd_rn(__dmul_rn(s_samp[j + 1], z1), tsh) : CUDART_INF;
-                    int guard = 0;
-                    while (tj > t && j > lo && guard < 8) {
-                        --j; tj1 = tj; tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh); ++guard;
-                    }
-                    while (j < hi && tj1 <= t && guard < 8) {
-                        ++j; tj = tj1;
-                        tj1 = (j < hi) ? __dadd_rn(__dmul_rn(s_samp[j + 1], z1), tsh) : CUDART_INF;
-                        ++guard;
-                    }
-                    if (!(tj <= t && (j == hi || tj1 > t))) {  // cold: fall back to bisection
-                        j = locate(cfg, lo, hi, t, z1, tsh);
-                        tj = tobs_at(cfg, j, z1, tsh);
-                        tj1 = (j < hi) ? tobs_at(cfg, j + 1, z1, tsh) : CUDART_INF;
-                    }
-                    const double a0 = __dadd_rn(__dadd_rn(node_mag_k<K>(bp, j, cp), ps.dm), ps.zc);
-                    if (j == hi || tj == t) {
-                        mu = a0;
+    if constexpr (FAST) {
+        const float2* __restrict__ bq = reinterpret_cast<const float2*>(bp);
+        const int T = cfg.T;
+        const float ga = ps.ga, gb = ps.gb, dmz = ps.dmz;
+        const float dlt = cfg.fast_delta, dhi = 1.0f - cfg.fast_delta;
+        float c[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) c[i] = (float)cp[i];
+        for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
+            const int g = cfg.f_glist[gi];
+            const int k1 = cfg.g_off[g + 1];
+            for (int k = cfg.g_off[g]; k < k1; ++k) {
+                const double* rec = s_obs + k * kObsRec;
+                const float4 rf = *reinterpret_cast<const float4*>(rec + 6);  // (float)t, (float)mag, 1/sigma, log(sigma)+C
+                const int simple = *reinterpret_cast<const int*>(rec + 8);
+                const double t = rec[0];
+                const float gq = fmaf(rf.x, ga, gb);
+                int j = __float2int_rd(gq);
+                const float fr = gq - (float)j;
+                bool inr = true;
+                double tj;
+                if (j >= lo && j < hi && fr > dlt && fr < dhi) {
+                    tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh);
+                } else {  // cold: range ends and near-node cases, settled with the exact comparisons
+                    const double tlo = __dadd_rn(__dmul_rn(s_samp[lo], z1), tsh);
+                    const double thi = __dadd_rn(__dmul_rn(s_samp[hi], z1), tsh);
+                    if (!(t >= tlo && t <= thi)) {
+                        inr = false;  // np.interp left = right = +inf
+                        tj = 0.0; j = lo;
                     } else {
-                        const double a1 = __dadd_rn(__dadd_rn(node_mag_k<K>(bp, j + 1, cp), ps.dm), ps.zc);
-                        // slope * (t - tj) + a0 with the interpolation weight in fp32: the weight only
-                        // scales (a1 - a0) <~ 1 mag, so its 6e-8 relative error is < 1e-7 mag
-                        const float wgt = __fdividef((float)__dsub_rn(t, tj), (float)__dsub_rn(tj1, tj));
-                        mu = fma(__dsub_rn(a1, a0), (double)wgt, a0);
-                        if (isnan(mu) && a0 == a1) mu = a0;
+                        j = locate(cfg, lo, hi, t, z1, tsh);
+                        if (j >= hi) j = hi - 1;  // t == t_hi: weight 1 on the last interval
+                        tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh);
                     }
                 }
-            } else {
+                float mu = CUDART_INF_F;
+                if (inr) {
+                    const float wgt = (float)__dsub_rn(t, tj) * ga;
+                    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+                        const float2 v = bq[i * T + j];
+                        d0 = fmaf(v.x, c[i], d0);
+                        d1 = fmaf(v.y, c[i], d1);
+                    }
+                    const float2 sc = bq[K * T + j], mn = bq[(K + 1) * T + j];
+                    const float a0 = fmaf(d0, sc.x, mn.x), a1 = fmaf(d1, sc.y, mn.y);
+                    mu = fmaf(wgt, a1 - a0, a0) + dmz;
+                }
+                if (simple) {
+                    // truncnorm.logpdf with b = +inf = the plain Gaussian log-density; mu = +inf gives -inf here where
+                    // SciPy gives NaN: both end as the sentinel (core/base.py:180-181)
+                    const float xq = (rf.y - mu) * rf.z;
+                    lsum += (double)fmaf(-0.5f * xq, xq, -rf.w);
+                } else {
+                    const double so = rec[2];
+                    const double mud = (double)mu;
+                    if (cfg.sy_mode[g] == 0 && isfinite(so)) lsum += obs_term_static_det(rec[1], mud, rec[3], rec[5], cfg.g_lim[g]);
+                    else lsum += obs_term(rec[1], mud, so, sys_sigma(cfg, g, t, row), cfg.g_lim[g]);
+                }
+            }
+        }
+    } else {
+        for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
+            const int g = cfg.f_glist[gi];
+            const double lim = cfg.g_lim[g];
+            const int mode = cfg.sy_mode[g];
+            const int k1 = cfg.g_off[g + 1];
+            for (int k = cfg.g_off[g]; k < k1; ++k) {
+                const double* rec = s_obs + k * kObsRec;  // t, mag, sigma_obs, sigma, 1/sigma, log(sigma)+C
+                const double t = rec[0], m = rec[1], so = rec[2];
                 auto node = [&](int j) { return node_mag_k<K>(bp, j, cp); };
                 auto abs_at = [&](int s) { return sample_mag(cfg, f, s, node); };
-                mu = interp_obs(cfg, f, t, ps, abs_at);
+                const double mu = interp_obs(cfg, f, t, ps, abs_at);
+                if (mode == 0 && isfinite(so)) lsum += obs_term_static_det(m, mu, rec[3], rec[5], lim);
+                else lsum += obs_term(m, mu, so, sys_sigma(cfg, g, t, row), lim);
             }
-            double term;
-            if (FAST && mode == 0 && lim == CUDART_INF && isfinite(so)) {
-                // truncnorm.logpdf with b = +inf: NaN when mu is +inf/NaN (b = inf - inf), else the
-                // plain Gaussian log-density with the staged 1/sigma and log(sigma) + log(2 pi)/2
-                const double xq = __dsub_rn(m, mu) * rec[4];
-                term = (mu < CUDART_INF) ? (-0.5 * (xq * xq) - rec[5]) : CUDART_NAN;
-            } else if (mode == 0 && isfinite(so)) {
-                term = obs_term_static_det(m, mu, rec[3], rec[5], lim);
-            } else {
-                term = obs_term(m, mu, so, sys_sigma(cfg, g, t, row), lim);
-            }
-            lsum += term;
         }
     }
     return lsum;
+}
+
+// Source of the per-filter basis pack a fused kernel stages into shared memory (same byte count either way).
+template <bool FAST>
+__device__ __forceinline__ const double* basis_src(const DevCfg& cfg, int f, int K) {
+    const size_t off = (size_t)f * cfg.T * (K + 2);
+    return FAST ? reinterpret_cast<const double*>(cfg.bpack32) + off : cfg.bpack + off;
 }
 
 // FAST = sample grid is the (uniform) training grid itself: stage 1 is the identity and the
@@ -426,7 +474,7 @@ fused_mlp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long lon
     auto issue_b = [&](long long qb) {
         const int f = (int)(qb % F);
         mbar_arrive_expect_tx(full_b, bbytes);
-        bulk_g2s(s_basis, cfg.bpack + (size_t)f * cfg.T * (K + 2), bbytes, full_b);
+        bulk_g2s(s_basis, basis_src<FAST>(cfg, f, K), bbytes, full_b);
     };
 
     if (tid == 0) {
@@ -544,17 +592,23 @@ fused_mlp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long lon
             mbar_wait(full_b, (uint32_t)(qb & 1));
 #pragma unroll
             for (int p = 0; p < PT; ++p) {
-                // coefficients: + b2 in fp32 (Keras Dense), then fp64 for the rest
-                double cp[K];
+                // coefficients: + b2 in fp32 (Keras Dense)
+                float cf[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float cf = ctot[p][k] + cfg.b2[f * K + k];
-                    ok[p] = ok[p] && isfinite(cf);
-                    cp[k] = (double)cf;
+                    cf[k] = ctot[p][k] + cfg.b2[f * K + k];
+                    ok[p] = ok[p] && isfinite(cf[k]);
                 }
                 if (!ok[p]) continue;
-                logl[p] += fused_filter_logl<K, FAST>(cfg, f, cp, ps[p], pts + (live[p] ? n[p] : 0) * cfg.P, s_basis, s_obs,
-                                                      s_samp);
+                const double* prow = pts + (live[p] ? n[p] : 0) * cfg.P;
+                if constexpr (FAST) {
+                    logl[p] += fused_filter_logl<K, true>(cfg, f, cf, ps[p], prow, s_basis, s_obs, s_samp);
+                } else {
+                    double cp[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) cp[k] = (double)cf[k];
+                    logl[p] += fused_filter_logl<K, false>(cfg, f, cp, ps[p], prow, s_basis, s_obs, s_samp);
+                }
             }
             // release the basis pack; the last warp to arrive loads the next filter's pack
             __syncwarp();

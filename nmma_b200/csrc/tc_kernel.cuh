@@ -255,7 +255,8 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float h = fmaxf(__uint_as_float(v[j]), 0.f);
+                        const float vj = __uint_as_float(v[j]);
+                        const float h = vj + fabsf(vj);  // 2 relu(v) on the FMA pipe; W2 is staged halved (api.cu)
                         const float hh = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
                         v[j] = __float_as_uint(h);
                         lo[j] = __float_as_uint(h - hh);
@@ -378,7 +379,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             mbar_wait(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&bars->b_full[slot], bbytes);
-                bulk_g2s(s_basis0 + slot * bslot, cfg.bpack + (size_t)f * cfg.T * (K + 2), bbytes, &bars->b_full[slot]);
+                bulk_g2s(s_basis0 + slot * bslot, basis_src<FAST>(cfg, f, K), bbytes, &bars->b_full[slot]);
             }
             __syncwarp();
             const float* src = cfg.tcpack + (size_t)f * NCH * kTcChunkFloats;
@@ -414,19 +415,26 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 const uint32_t par = (vseq >> 1) & 1;
                 mbar_wait(&bars->c_full[t][slot], par);
                 const float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
-                double cp[K];
+                float cf[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float cf = cb[k * kTcTile];
-                    ok = ok && isfinite(cf);
-                    cp[k] = (double)cf;
+                    cf[k] = cb[k * kTcTile];
+                    ok = ok && isfinite(cf[k]);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->c_free[t][slot]);
                 mbar_wait(&bars->b_full[slot], par);
-                if (ok)
-                    logl += fused_filter_logl<K, FAST>(cfg, f, cp, ps, row,
-                                                       reinterpret_cast<const double*>(s_basis0 + slot * bslot), s_obs, s_samp);
+                if (ok) {
+                    const double* basis = reinterpret_cast<const double*>(s_basis0 + slot * bslot);
+                    if constexpr (FAST) {
+                        logl += fused_filter_logl<K, true>(cfg, f, cf, ps, row, basis, s_obs, s_samp);
+                    } else {
+                        double cp[K];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) cp[k] = (double)cf[k];
+                        logl += fused_filter_logl<K, false>(cfg, f, cp, ps, row, basis, s_obs, s_samp);
+                    }
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->b_free[slot]);
             }
