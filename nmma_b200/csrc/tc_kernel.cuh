@@ -8,9 +8,13 @@
 // round-toward-zero (profiles/r01_tc_probe.txt), so the large layer-2 products h_hi*W_hi accumulate in chains of 16
 // MMAs (one 128-hidden group) whose partials the CUDA cores sum with round-to-nearest adds; the two cross terms are
 // 2^-11 smaller and accumulate over the whole filter in a separate accumulator, where the truncation bias is below
-// 2e-8 relative.  Reading a partial per group instead of per chunk matters: the kernel is bound by TMEM read
-// bandwidth (tcgen05.ld, 64 B/clk/SM; profiles/r01_fused_tc_v2_summary.json), and the layer-1 accumulators alone
-// are 4 B per hidden unit and point.
+// 2e-8 relative.
+//
+// What bounds it (profiles/r01_tc_experiments.md): not the tensor pipe (30 % active), not TMEM bandwidth (tools/tmem_bw.cu:
+// > 600 B/clk/SM for the ld + 2 st mix, the kernel moves ~60), not the ALU work (removing it changes nothing) and not the
+// back end, but the latency of the per-chunk hand-offs (mbarrier wake-up, tcgen05.ld / st + wait, tcgen05.commit): the
+// bare skeleton of one 32-hidden chunk costs ~700 cycles per tile against 144 cycles of MMA work.  A faster version has
+// to do several times more work per hand-off, not fewer instructions per chunk.
 //
 // Work decomposition (one persistent CTA per SM, 20 warps, two 128-point tiles in flight):
 //   warps 0-3 / 4-7    activation warps of tile 0 / 1: thread = one parameter point = one TMEM lane.  Per filter they
@@ -253,6 +257,8 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     tc_fence_after();
                     tmem_ld32(tbase + kColD1 + 32 * b, v);
                     tmem_wait_ld();
+#ifndef TCV_NO_ALU   // TCV_*: compile-time timing experiments (tools/build_variants.py, profiles/r01_tc_experiments.md);
+                     // a library built with any of them returns wrong numbers and only serves to time the skeleton
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float vj = __uint_as_float(v[j]);
@@ -261,6 +267,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                         v[j] = __float_as_uint(h);
                         lo[j] = __float_as_uint(h - hh);
                     }
+#else
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) lo[j] = v[j];
+#endif
                     if (c >= 2) {
                         // L2 of chunk c-2 done: its A2 buffer is free; if it closed a group, the partial is complete
                         mbar_wait(&bars->a2_free[t][b], (u - 1) & 1);
@@ -274,7 +284,9 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                         }
                     }
                     tmem_st32(tbase + kColA2H + 32 * b, v);
+#ifndef TCV_NO_STLO
                     tmem_st32(tbase + kColA2L + 32 * b, lo);
+#endif
                     tmem_wait_st();
                     tc_fence_before();  // orders the D1 / D2 loads and the A2 stores before the issuer's next MMAs
                     __syncwarp();
@@ -322,8 +334,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         auto adv2 = [&]() { lo2 += kSlotStep; if (++s2 == kTcStages) { s2 = 0; lo2 = (uint32_t)dB2; } };
         auto l1 = [&](int b) {  // D1[b] = A1 . B1(slot s1)   (elected lane only)
             mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, lo1, hi1, id1, 0u);
+#ifndef TCV_NO_L1X
             mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1L, lo1, hi1, id1, 1u);
             mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, lo1 + (1024 >> 4), hi1, id1, 1u);
+#endif
             tc_commit(&bars->d1_full[t][b]);
         };
         uint32_t vseq = 0;
@@ -354,8 +368,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
 #pragma unroll
                         for (int s = 0; s < 4; ++s) {
                             mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : gfirst);
+#ifndef TCV_NO_L2X
                             mma_tf32_ts(dx, al + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : ffirst);
                             mma_tf32_ts(dx, ah + 8 * s, lo2 + s * 32 + (2048 >> 4), hi2, id2, 1u);
+#endif
                         }
                         tc_commit(&bars->a2_free[t][b]);
                         tc_commit(&bars->w_free[s2]);
@@ -386,9 +402,13 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             for (int c = 0; c < NCH; ++c) {
                 mbar_wait(&bars->w_free[st], ph ^ 1);
                 if (elect_one()) {
+#ifdef TCV_NO_WLOAD
+                    mbar_arrive(&bars->w_full[st]);
+#else
                     mbar_arrive_expect_tx(&bars->w_full[st], kTcChunkBytes);
                     bulk_g2s(wring + (size_t)st * kTcChunkFloats, src + (size_t)c * kTcChunkFloats, kTcChunkBytes,
                              &bars->w_full[st]);
+#endif
                 }
                 __syncwarp();
                 if (++st == kTcStages) { st = 0; ph ^= 1; }
@@ -426,6 +446,11 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 mbar_wait(&bars->b_full[slot], par);
                 if (ok) {
                     const double* basis = reinterpret_cast<const double*>(s_basis0 + slot * bslot);
+#ifdef TCV_NO_BACKEND
+                    if (true) {
+                        logl += cf[0];
+                    } else
+#endif
                     if constexpr (FAST) {
                         logl += fused_filter_logl<K, true>(cfg, f, cf, ps, row, basis, s_obs, s_samp);
                     } else {
