@@ -241,15 +241,15 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                     const int n = j % kTcChunk;
                     for (int k = 0; k <= d; ++k) {
                         const float w = (k < d) ? h->W1[((size_t)f * d + k) * H + j] : h->b1[(size_t)f * H + j];
-                        tf32_split(w, &ch[tc_b_index(kTcChunk, n, k)], &ch[256 + tc_b_index(kTcChunk, n, k)]);
+                        tf32_split(w, &ch[tc_b_index(kTcChunk, n, k)], &ch[kTcB1Floats + tc_b_index(kTcChunk, n, k)]);
                     }
                     const int s = n / 8, kk = n % 8;
                     for (int o = 0; o < K; ++o) {
                         // halved (exact): the activation warps hand over 2 relu(v) = v + |v|, one FADD on the FMA pipe
                         // instead of an FMNMX on the half-rate ALU pipe; products and sums are bit-identical
                         const float w = 0.5f * h->W2[((size_t)f * H + j) * K + o];
-                        tf32_split(w, &ch[512 + s * 128 + tc_b_index(kTcN2, o, kk)],
-                                   &ch[1024 + s * 128 + tc_b_index(kTcN2, o, kk)]);
+                        tf32_split(w, &ch[2 * kTcB1Floats + s * 128 + tc_b_index(kTcN2, o, kk)],
+                                   &ch[2 * kTcB1Floats + kTcB2Floats + s * 128 + tc_b_index(kTcN2, o, kk)]);
                     }
                 }
             if (int rc = upload(h, tp, &c.tcpack)) return rc;
@@ -791,7 +791,7 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
     } else if (k == "tc_executed_flop_per_eval") {
         // tensor-core kernel: per 32-hidden chunk and point 3 layer-1 MMAs (N=32, K=8) + 12 layer-2 MMAs (N=16, K=8)
         if (int rc = finalize(h, false)) return rc;
-        *value = (int64_t)h->F * h->cfg.tc_nch * (3LL * 2 * kTcChunk * 8 + 12LL * 2 * kTcN2 * 8);
+        *value = (int64_t)h->F * h->cfg.tc_nch * (3LL * 2 * kTcChunk * 8 + 3LL * kTcKSteps * 2 * kTcN2 * 8);
     } else return fail(h, NMMA_B200_ERR_ARG, "unknown info key '%s'", key);
     return NMMA_B200_OK;
 }

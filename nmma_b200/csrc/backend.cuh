@@ -36,8 +36,8 @@ struct DevCfg {
     // MLP front end
     const float* wpack;   // F*HP*RW: row j = [W1[0..d-1][j], b1[j], W2[j][0..K-1], 0-pad]
     const float* b2;      // F*K
-    // tensor-core front end: per (filter, 32-hidden chunk) 1536 floats = B1hi | B1lo | B2hi | B2lo operand tiles
-    const float* tcpack;  // F*tc_nch*1536
+    // tensor-core front end: per (filter, 48-hidden chunk) kTcChunkFloats = B1hi | B1lo | B2hi | B2lo operand tiles
+    const float* tcpack;  // F*tc_nch*kTcChunkFloats
     int tc_nch;           // chunks per filter (even)
     // hybrid front end (hy_kernel.cuh): per (filter, 64-hidden group) [W1/b1 hidden-pair rows | W2 hi tiles | W2 lo tiles]
     const float* hypack;

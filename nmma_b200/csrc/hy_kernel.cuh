@@ -63,14 +63,6 @@ struct HyBars {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
-            "r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-        : "memory");
-}
-
 // shared-window (32-bit) addressing for the hot loop: keeps ptxas from re-deriving the window base (S2UR) per access
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
     uint32_t ok;

@@ -5,30 +5,31 @@
 // (profiles/r01_tc_numerics.txt); with a = a_hi + a_lo, b = b_hi + b_lo (hi = top 19 bits, which is exactly what the
 // tensor core reads from an fp32 operand of kind::tf32) the three products a_hi*b_hi + a_lo*b_hi + a_hi*b_lo carry
 // ~2^-21 relative error, the same order as fp32 FFMA.  The tensor core adds into its fp32 accumulator with
-// round-toward-zero (profiles/r01_tc_probe.txt), so the large layer-2 products h_hi*W_hi accumulate in chains of 16
-// MMAs (one 128-hidden group) whose partials the CUDA cores sum with round-to-nearest adds; the two cross terms are
+// round-toward-zero (profiles/r01_tc_probe.txt), so the large layer-2 products h_hi*W_hi accumulate in chains of 12
+// MMAs (one 96-hidden group) whose partials the CUDA cores sum with round-to-nearest adds; the two cross terms are
 // 2^-11 smaller and accumulate over the whole filter in a separate accumulator, where the truncation bias is below
 // 2e-8 relative.
 //
 // What bounds it (profiles/r01_tc_experiments.md): not the tensor pipe (30 % active), not TMEM bandwidth (tools/tmem_bw.cu:
-// > 600 B/clk/SM for the ld + 2 st mix, the kernel moves ~60), not the ALU work (removing it changes nothing) and not the
-// back end, but the latency of the per-chunk hand-offs (mbarrier wake-up, tcgen05.ld / st + wait, tcgen05.commit): the
-// bare skeleton of one 32-hidden chunk costs ~700 cycles per tile against 144 cycles of MMA work.  A faster version has
-// to do several times more work per hand-off, not fewer instructions per chunk.
+// > 600 B/clk/SM for the ld + 2 st mix, the kernel moves ~60) and not the back end, but the latency of the per-chunk
+// hand-offs (mbarrier wake-up, tcgen05.ld / st + wait, tcgen05.commit): the bare skeleton of one chunk step costs ~700
+// cycles per tile.  Hence the chunk is as wide as TMEM allows: 48 hidden units, with h written back in place over the
+// layer-1 accumulator (32-hidden chunks with a separate h buffer: 151 M evals/s; 48 in place: 173 M).
 //
 // Work decomposition (one persistent CTA per SM, 20 warps, two 128-point tiles in flight):
 //   warps 0-3 / 4-7    activation warps of tile 0 / 1: thread = one parameter point = one TMEM lane.  Per filter they
-//                      write the scaled inputs as the layer-1 A operand (TMEM); per 32-hidden chunk they read the
-//                      layer-1 accumulator (tcgen05.ld), apply ReLU, split into hi/lo, write the layer-2 A operand back
-//                      to TMEM (tcgen05.st) and sum the layer-2 chunk partials; the K coefficients go to shared memory.
-//   warps 8 / 9        MMA issuer of tile 0 / 1 (one elected lane): per chunk D2 = [h_hi | h_lo] . W2^T (12 MMAs,
-//                      128x16x8) and, two chunks ahead, D1 = [x_hi,1 | x_lo] . [W1;b1]^T (3 MMAs, 128x32x8); A from
+//                      write the scaled inputs as the layer-1 A operand (TMEM); per 48-hidden chunk they read the
+//                      layer-1 accumulator (tcgen05.ld), apply ReLU, split into hi/lo, write h back in place and h_lo
+//                      beside it (tcgen05.st, the layer-2 A operands) and sum the layer-2 group partials; the K
+//                      coefficients go to shared memory.
+//   warps 8 / 9        MMA issuer of tile 0 / 1 (one elected lane): per chunk D2 = [h_hi | h_lo] . W2^T (18 MMAs,
+//                      128x16x8) and, two chunks ahead, D1 = [x_hi,1 | x_lo] . [W1;b1]^T (3 MMAs, 128x48x8); A from
 //                      TMEM, B from shared memory.
-//   warp 10            TMA producer: 6 KB weight chunks (cp.async.bulk) into a shared-memory ring, basis packs per filter.
+//   warp 10            TMA producer: 9 KB weight chunks (cp.async.bulk) into a shared-memory ring, basis packs per filter.
 //   warp 11            TMEM allocation / release.
-//   warps 12-15/16-19  back-end warps of tile 0 / 1: thread = one point; fp64 reconstruction, interpolation and
-//                      likelihood for the filter whose coefficients the activation warps just finished, overlapping
-//                      the next filter's MLP.
+//   warps 12-15/16-19  back-end warps of tile 0 / 1: thread = one point; reconstruction, interpolation and likelihood
+//                      (kernels.cuh: fused_filter_logl) for the filter whose coefficients the activation warps just
+//                      finished, overlapping the next filter's MLP.
 // All hand-offs are mbarriers (tcgen05.commit for MMA completion); nothing spins on memory.
 #pragma once
 #include "kernels.cuh"
@@ -40,18 +41,24 @@ constexpr int kTcActWarps = 8;
 constexpr int kTcBackWarp0 = 12;
 constexpr int kTcTile = 128;                 // points per tile = TMEM lanes
 constexpr int kTcTiles = 2;                  // tiles in flight per CTA
-constexpr int kTcChunk = 32;                 // hidden units per chunk
-constexpr int kTcChunkFloats = 1536;         // B1hi 256 | B1lo 256 | B2hi 512 | B2lo 512
-constexpr uint32_t kTcChunkBytes = kTcChunkFloats * 4;
-constexpr int kTcStages = 12;                // weight ring depth (72 KB)
+constexpr int kTcChunk = 48;                 // hidden units per chunk = per act <-> issuer hand-off (N of the layer-1 MMA)
+constexpr int kTcBlk = 16;                   // columns per ReLU/split/store block of the activation warps (8: -1 %, 32+16: -2 %)
+constexpr int kTcKSteps = kTcChunk / 8;      // layer-2 MMAs (K = 8) per chunk and split term
 constexpr int kTcN2 = 16;                    // layer-2 MMA N (n_coeff padded)
-// TMEM columns of one tile (tile t at column 256 t)
-constexpr uint32_t kColD1 = 0;               // 2 x 32  layer-1 accumulators
-constexpr uint32_t kColA2H = 64;             // 2 x 32  relu(h) (the tensor core reads its top 19 bits = h_hi)
-constexpr uint32_t kColA2L = 128;            // 2 x 32  h_lo
-constexpr uint32_t kColD2 = 192;             // 2 x 16  layer-2 h_hi*W_hi partials, double buffered by 4-chunk group
+constexpr int kTcB1Floats = kTcChunk * 8;    // one layer-1 B tile: [48 hidden] x [8 = d inputs, bias, pad]
+constexpr int kTcB2Floats = kTcKSteps * kTcN2 * 8;   // layer-2 B tiles of one chunk: 6 k-steps x [16 coeff] x [8 hidden]
+constexpr int kTcChunkFloats = 2 * kTcB1Floats + 2 * kTcB2Floats;   // B1hi | B1lo | B2hi | B2lo = 2304 floats (9 KB)
+constexpr uint32_t kTcChunkBytes = kTcChunkFloats * 4;
+constexpr int kTcStages = 8;                 // weight ring depth (72 KB)
+// TMEM columns of one tile (tile t at column 256 t).  The hand-off latency per chunk is fixed (~700 cycles,
+// profiles/r01_tc_experiments.md), so the chunk is as wide as 256 columns allow: h goes back IN PLACE over the layer-1
+// accumulator it came from, which leaves room for 2 buffers of 48 instead of 32 hidden units.
+constexpr uint32_t kColD1 = 0;               // 2 x 48  layer-1 accumulators, overwritten by 2 relu(h) (the tensor core reads
+                                             //         its top 19 bits = h_hi as the layer-2 A operand)
+constexpr uint32_t kColA2L = 96;             // 2 x 48  h_lo
+constexpr uint32_t kColD2 = 192;             // 2 x 16  layer-2 h_hi*W_hi partials, double buffered by accumulation group
 constexpr uint32_t kColD2X = 240;            // 16      layer-2 cross terms h_lo*W_hi + h_hi*W_lo of the whole filter
-constexpr int kTcGroup = 4;                  // chunks per layer-2 accumulation chain
+constexpr int kTcGroup = 2;                  // chunks per layer-2 accumulation chain (12 MMAs, RZ accumulate)
 constexpr uint32_t kColA1H = 224;            // 8       [x_hi, 1, 0..]
 constexpr uint32_t kColA1L = 232;            // 8       [x_lo, 0, 0..]
 
@@ -91,6 +98,15 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// v <- 2 relu(v) (= v + |v|: one FADD on the FMA pipe instead of an FMNMX on the half-rate ALU pipe; W2 is staged halved,
+// api.cu), lo <- its low part below the 19 bits the tensor core reads.
+__device__ __forceinline__ void relu_split(uint32_t& v, uint32_t& lo) {
+    const float vj = __uint_as_float(v);
+    const float h = vj + fabsf(vj);
+    const float hh = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
+    v = __float_as_uint(h);
+    lo = __float_as_uint(h - hh);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* v) {
@@ -106,6 +122,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t* v) {
         "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
         "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
         "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
@@ -252,27 +275,15 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 for (int c = 0; c < NCH; ++c) {
                     const int b = c & 1;
                     const uint32_t u = ubase + ((uint32_t)c >> 1);
-                    uint32_t v[32], lo[32];
+                    uint32_t v[kTcChunk];
                     mbar_wait(&bars->d1_full[t][b], u & 1);
                     tc_fence_after();
-                    tmem_ld32(tbase + kColD1 + 32 * b, v);
+                    tmem_ld32(tbase + kColD1 + kTcChunk * b, v);
+                    tmem_ld16(tbase + kColD1 + kTcChunk * b + 32, v + 32);
                     tmem_wait_ld();
-#ifndef TCV_NO_ALU   // TCV_*: compile-time timing experiments (tools/build_variants.py, profiles/r01_tc_experiments.md);
-                     // a library built with any of them returns wrong numbers and only serves to time the skeleton
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float vj = __uint_as_float(v[j]);
-                        const float h = vj + fabsf(vj);  // 2 relu(v) on the FMA pipe; W2 is staged halved (api.cu)
-                        const float hh = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
-                        v[j] = __float_as_uint(h);
-                        lo[j] = __float_as_uint(h - hh);
-                    }
-#else
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) lo[j] = v[j];
-#endif
                     if (c >= 2) {
-                        // L2 of chunk c-2 done: its A2 buffer is free; if it closed a group, the partial is complete
+                        // L2 of chunk c-2 done: its h_lo buffer is free (D1[b] was already rewritten by layer 1 of this
+                        // chunk, queued behind it); if it closed a group, the partial is complete
                         mbar_wait(&bars->a2_free[t][b], (u - 1) & 1);
                         tc_fence_after();
                         if (((c - 2) & (kTcGroup - 1)) == kTcGroup - 1) {
@@ -283,12 +294,26 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                             for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
                         }
                     }
-                    tmem_st32(tbase + kColA2H + 32 * b, v);
-#ifndef TCV_NO_STLO
-                    tmem_st32(tbase + kColA2L + 32 * b, lo);
+                    // ReLU + hi/lo split in kTcBlk-column blocks, h back in place and h_lo beside it: the stores of one block
+                    // are in flight while the next block is computed (16 live h_lo registers)
+#pragma unroll
+                    for (int blk = 0; blk < kTcChunk / kTcBlk; ++blk) {
+                        uint32_t lo[kTcBlk];
+#ifndef TCV_NO_ALU   // TCV_*: compile-time timing experiments (tools/build_variants.py, profiles/r01_tc_experiments.md);
+                     // a library built with any of them returns wrong numbers and only serves to time the skeleton
+#pragma unroll
+                        for (int j = 0; j < kTcBlk; ++j) relu_split(v[kTcBlk * blk + j], lo[j]);
+#else
+#pragma unroll
+                        for (int j = 0; j < kTcBlk; ++j) lo[j] = v[kTcBlk * blk + j];
 #endif
+                        tmem_st16(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, v + kTcBlk * blk);
+#ifndef TCV_NO_STLO
+                        tmem_st16(tbase + kColA2L + kTcChunk * b + kTcBlk * blk, lo);
+#endif
+                    }
                     tmem_wait_st();
-                    tc_fence_before();  // orders the D1 / D2 loads and the A2 stores before the issuer's next MMAs
+                    tc_fence_before();  // orders the D1 / D2 loads and the operand stores before the issuer's next MMAs
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->a2_full[t][b]);
                 }
@@ -315,7 +340,8 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 if (lane == 0) mbar_arrive(&bars->c_full[t][slot]);
             }
         }
-    } else if (warp < kTcActWarps + kTcTiles) {
+    } else if (warp < kTcBackWarp0) {
+      if (warp < kTcActWarps + kTcTiles) {
         // =====================================================================================================
         // MMA issuer of tile t.  Ring cursors advance incrementally; descriptors differ only in their low word.
         // =====================================================================================================
@@ -323,7 +349,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         constexpr uint32_t id1 = tc_idesc(kTcChunk), id2 = tc_idesc(kTcN2);
         const uint32_t wbase = smem_u32(wring);
         const uint64_t dB1 = tc_smem_desc(wbase, kTcChunk * 16, 128);
-        const uint64_t dB2 = tc_smem_desc(wbase + 2048, kTcN2 * 16, 128);
+        const uint64_t dB2 = tc_smem_desc(wbase + 2 * kTcB1Floats * 4, kTcN2 * 16, 128);
         const uint32_t hi1 = (uint32_t)(dB1 >> 32), hi2 = (uint32_t)(dB2 >> 32);
         constexpr uint32_t kSlotStep = kTcChunkBytes >> 4;
         uint32_t s1 = 0, p1 = 0;                    // ring slot / phase parity of the next chunk layer 1 consumes
@@ -333,10 +359,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         auto adv1 = [&]() { lo1 += kSlotStep; if (++s1 == kTcStages) { s1 = 0; p1 ^= 1; lo1 = (uint32_t)dB1; } };
         auto adv2 = [&]() { lo2 += kSlotStep; if (++s2 == kTcStages) { s2 = 0; lo2 = (uint32_t)dB2; } };
         auto l1 = [&](int b) {  // D1[b] = A1 . B1(slot s1)   (elected lane only)
-            mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, lo1, hi1, id1, 0u);
+            mma_tf32_ts(tb + kColD1 + kTcChunk * b, tb + kColA1H, lo1, hi1, id1, 0u);
 #ifndef TCV_NO_L1X
-            mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1L, lo1, hi1, id1, 1u);
-            mma_tf32_ts(tb + kColD1 + 32 * b, tb + kColA1H, lo1 + (1024 >> 4), hi1, id1, 1u);
+            mma_tf32_ts(tb + kColD1 + kTcChunk * b, tb + kColA1L, lo1, hi1, id1, 1u);
+            mma_tf32_ts(tb + kColD1 + kTcChunk * b, tb + kColA1H, lo1 + ((kTcB1Floats * 4) >> 4), hi1, id1, 1u);
 #endif
             tc_commit(&bars->d1_full[t][b]);
         };
@@ -363,14 +389,14 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     if (elect_one()) {
                         const int cc = c + b;
                         const uint32_t d2 = tb + kColD2 + 16 * ((cc / kTcGroup) & 1), dx = tb + kColD2X;
-                        const uint32_t ah = tb + kColA2H + 32 * b, al = tb + kColA2L + 32 * b;
+                        const uint32_t ah = tb + kColD1 + kTcChunk * b, al = tb + kColA2L + kTcChunk * b;
                         const uint32_t gfirst = (cc & (kTcGroup - 1)) == 0 ? 0u : 1u, ffirst = cc == 0 ? 0u : 1u;
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) {
+                        for (int s = 0; s < kTcKSteps; ++s) {   // one k-step = 8 hidden units = a 512-byte B tile
                             mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : gfirst);
 #ifndef TCV_NO_L2X
                             mma_tf32_ts(dx, al + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : ffirst);
-                            mma_tf32_ts(dx, ah + 8 * s, lo2 + s * 32 + (2048 >> 4), hi2, id2, 1u);
+                            mma_tf32_ts(dx, ah + 8 * s, lo2 + s * 32 + ((kTcB2Floats * 4) >> 4), hi2, id2, 1u);
 #endif
                         }
                         tc_commit(&bars->a2_free[t][b]);
@@ -383,7 +409,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 }
             }
         }
-    } else if (warp == 10) {
+      } else if (warp == 10) {
         // =====================================================================================================
         // TMA producer
         // =====================================================================================================
@@ -415,7 +441,8 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             }
             if (++f == F) f = 0;
         }
-    } else if (warp >= kTcBackWarp0) {
+      }
+    } else {
         // =====================================================================================================
         // back-end warps: fp64 likelihood of filter f while the tensor cores work on filter f + 1
         // =====================================================================================================
