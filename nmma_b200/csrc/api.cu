@@ -1,6 +1,8 @@
 // C-ABI implementation (include/nmma_b200.h): handle, one-time staging of the
 // surrogate / observation tables into device buffers, and kernel dispatch.
 #define NMMA_TWO_STAGE_TU 1  // this translation unit owns the non-template two-stage kernels
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -248,8 +250,12 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                         // halved (exact): the activation warps hand over 2 relu(v) = v + |v|, one FADD on the FMA pipe
                         // instead of an FMNMX on the half-rate ALU pipe; products and sums are bit-identical
                         const float w = 0.5f * h->W2[((size_t)f * H + j) * K + o];
-                        tf32_split(w, &ch[2 * kTcB1Floats + s * 128 + tc_b_index(kTcN2, o, kk)],
-                                   &ch[2 * kTcB1Floats + kTcB2Floats + s * 128 + tc_b_index(kTcN2, o, kk)]);
+                        float* whi = &ch[2 * kTcB1Floats + s * 128 + tc_b_index(kTcN2, o, kk)];
+                        tf32_split(w, whi, &ch[2 * kTcB1Floats + kTcB2Floats + s * 128 + tc_b_index(kTcN2, o, kk)]);
+                        // fp16 copy of W_hi for the h_lo W_hi term (kind::f16, K = 16): W_hi has 11 significant bits, so the
+                        // copy is exact unless |w| < 2^-14
+                        __half* hb = reinterpret_cast<__half*>(&ch[2 * kTcB1Floats + 2 * kTcB2Floats]);
+                        hb[(n / 16) * 256 + tc_b_index16(kTcN2, o, n % 16)] = __float2half_rn(*whi);
                     }
                 }
             if (int rc = upload(h, tp, &c.tcpack)) return rc;
@@ -791,7 +797,7 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
     } else if (k == "tc_executed_flop_per_eval") {
         // tensor-core kernel: per 32-hidden chunk and point 3 layer-1 MMAs (N=32, K=8) + 12 layer-2 MMAs (N=16, K=8)
         if (int rc = finalize(h, false)) return rc;
-        *value = (int64_t)h->F * h->cfg.tc_nch * (3LL * 2 * kTcChunk * 8 + 3LL * kTcKSteps * 2 * kTcN2 * 8);
+        *value = (int64_t)h->F * h->cfg.tc_nch * (3LL * 2 * kTcChunk * 8 + 2LL * kTcKSteps * 2 * kTcN2 * 8 + 1LL * kTcKSteps16 * 2 * kTcN2 * 16);
     } else return fail(h, NMMA_B200_ERR_ARG, "unknown info key '%s'", key);
     return NMMA_B200_OK;
 }

@@ -32,6 +32,8 @@
 //                      finished, overlapping the next filter's MLP.
 // All hand-offs are mbarriers (tcgen05.commit for MMA completion); nothing spins on memory.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace nmma {
@@ -41,21 +43,24 @@ constexpr int kTcActWarps = 8;
 constexpr int kTcBackWarp0 = 12;
 constexpr int kTcTile = 128;                 // points per tile = TMEM lanes
 constexpr int kTcTiles = 2;                  // tiles in flight per CTA
-constexpr int kTcChunk = 48;                 // hidden units per chunk = per act <-> issuer hand-off (N of the layer-1 MMA)
+constexpr int kTcChunk = 64;                 // hidden units per chunk = per act <-> issuer hand-off (N of the layer-1 MMA)
 constexpr int kTcBlk = 16;                   // columns per ReLU/split/store block of the activation warps (8: -1 %, 32+16: -2 %)
-constexpr int kTcKSteps = kTcChunk / 8;      // layer-2 MMAs (K = 8) per chunk and split term
+constexpr int kTcKSteps = kTcChunk / 8;      // kind::tf32 layer-2 MMAs (K = 8) per chunk and term
+constexpr int kTcKSteps16 = kTcChunk / 16;   // kind::f16 layer-2 MMAs (K = 16) per chunk
 constexpr int kTcN2 = 16;                    // layer-2 MMA N (n_coeff padded)
-constexpr int kTcB1Floats = kTcChunk * 8;    // one layer-1 B tile: [48 hidden] x [8 = d inputs, bias, pad]
-constexpr int kTcB2Floats = kTcKSteps * kTcN2 * 8;   // layer-2 B tiles of one chunk: 6 k-steps x [16 coeff] x [8 hidden]
-constexpr int kTcChunkFloats = 2 * kTcB1Floats + 2 * kTcB2Floats;   // B1hi | B1lo | B2hi | B2lo = 2304 floats (9 KB)
+constexpr int kTcB1Floats = kTcChunk * 8;    // one layer-1 B tile: [64 hidden] x [8 = d inputs, bias, pad]
+constexpr int kTcB2Floats = kTcKSteps * kTcN2 * 8;      // tf32 layer-2 B tiles of one chunk: 8 k-steps x [16 coeff] x [8 hidden]
+constexpr int kTcB2HFloats = kTcKSteps16 * kTcN2 * 8;   // fp16 W_hi tiles: 4 k-steps x [16 coeff] x [16 hidden] halfs
+constexpr int kTcChunkFloats = 2 * kTcB1Floats + 2 * kTcB2Floats + kTcB2HFloats;   // B1hi | B1lo | B2hi | B2lo | B2hi(fp16) = 14 KB
 constexpr uint32_t kTcChunkBytes = kTcChunkFloats * 4;
-constexpr int kTcStages = 8;                 // weight ring depth (72 KB)
+constexpr int kTcStages = 6;                 // weight ring depth (84 KB)
 // TMEM columns of one tile (tile t at column 256 t).  The hand-off latency per chunk is fixed (~700 cycles,
 // profiles/r01_tc_experiments.md), so the chunk is as wide as 256 columns allow: h goes back IN PLACE over the layer-1
-// accumulator it came from, which leaves room for 2 buffers of 48 instead of 32 hidden units.
-constexpr uint32_t kColD1 = 0;               // 2 x 48  layer-1 accumulators, overwritten by 2 relu(h) (the tensor core reads
+// accumulator it came from, and h_lo (the 2^-11-relative remainder, which needs 11 bits, not 24) is packed as fp16
+// pairs and multiplied by an fp16 copy of W_hi with kind::f16 MMAs: 2 x (64 + 32) columns per tile.
+constexpr uint32_t kColD1 = 0;               // 2 x 64  layer-1 accumulators, overwritten by 2 relu(h) (the tensor core reads
                                              //         its top 19 bits = h_hi as the layer-2 A operand)
-constexpr uint32_t kColA2L = 96;             // 2 x 48  h_lo
+constexpr uint32_t kColA2L = 128;            // 2 x 32  h_lo as fp16 pairs (column j = hidden units 2j, 2j+1)
 constexpr uint32_t kColD2 = 192;             // 2 x 16  layer-2 h_hi*W_hi partials, double buffered by accumulation group
 constexpr uint32_t kColD2X = 240;            // 16      layer-2 cross terms h_lo*W_hi + h_hi*W_lo of the whole filter
 constexpr int kTcGroup = 2;                  // chunks per layer-2 accumulation chain (12 MMAs, RZ accumulate)
@@ -106,6 +111,16 @@ __device__ __forceinline__ void relu_split(uint32_t& v, uint32_t& lo) {
     const float hh = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
     v = __float_as_uint(h);
     lo = __float_as_uint(h - hh);
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -161,6 +176,12 @@ __host__ __device__ inline uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lb
 __host__ __device__ constexpr uint32_t tc_idesc(int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
+// kind::f16 instruction descriptor: fp32 accumulate, A/B fp16, both K-major, M = 128, K = 16.
+__host__ __device__ constexpr uint32_t tc_idesc_f16(int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+// half index of element (n, k) of an N x 16 fp16 B-operand tile (same core-matrix geometry: 8 rows x 16 bytes)
+__host__ __device__ constexpr int tc_b_index16(int N, int n, int k) { return (k >> 3) * (N * 8) + n * 8 + (k & 7); }
 // float index of element (n, k) of an N x 8 B-operand tile
 __host__ __device__ constexpr int tc_b_index(int N, int n, int k) { return (k >> 2) * (N * 4) + n * 4 + (k & 3); }
 
@@ -279,7 +300,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     mbar_wait(&bars->d1_full[t][b], u & 1);
                     tc_fence_after();
                     tmem_ld32(tbase + kColD1 + kTcChunk * b, v);
-                    tmem_ld16(tbase + kColD1 + kTcChunk * b + 32, v + 32);
+                    tmem_ld32(tbase + kColD1 + kTcChunk * b + 32, v + 32);
                     tmem_wait_ld();
                     if (c >= 2) {
                         // L2 of chunk c-2 done: its h_lo buffer is free (D1[b] was already rewritten by layer 1 of this
@@ -294,22 +315,28 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                             for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
                         }
                     }
-                    // ReLU + hi/lo split in kTcBlk-column blocks, h back in place and h_lo beside it: the stores of one block
-                    // are in flight while the next block is computed (16 live h_lo registers)
+                    // ReLU + hi/lo split in kTcBlk-column blocks, h back in place and h_lo (fp16 pairs) beside it: the stores
+                    // of one block are in flight while the next block is computed
 #pragma unroll
                     for (int blk = 0; blk < kTcChunk / kTcBlk; ++blk) {
-                        uint32_t lo[kTcBlk];
+                        uint32_t pk[kTcBlk / 2];
 #ifndef TCV_NO_ALU   // TCV_*: compile-time timing experiments (tools/build_variants.py, profiles/r01_tc_experiments.md);
                      // a library built with any of them returns wrong numbers and only serves to time the skeleton
 #pragma unroll
-                        for (int j = 0; j < kTcBlk; ++j) relu_split(v[kTcBlk * blk + j], lo[j]);
+                        for (int j = 0; j < kTcBlk; j += 2) {
+                            uint32_t l0, l1;
+                            relu_split(v[kTcBlk * blk + j], l0);
+                            relu_split(v[kTcBlk * blk + j + 1], l1);
+                            const __half2 hp = __floats2half2_rn(__uint_as_float(l0), __uint_as_float(l1));  // .x = low half
+                            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+                        }
 #else
 #pragma unroll
-                        for (int j = 0; j < kTcBlk; ++j) lo[j] = v[kTcBlk * blk + j];
+                        for (int j = 0; j < kTcBlk / 2; ++j) pk[j] = v[kTcBlk * blk + j];
 #endif
                         tmem_st16(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, v + kTcBlk * blk);
 #ifndef TCV_NO_STLO
-                        tmem_st16(tbase + kColA2L + kTcChunk * b + kTcBlk * blk, lo);
+                        tmem_st8(tbase + kColA2L + (kTcChunk / 2) * b + (kTcBlk / 2) * blk, pk);
 #endif
                     }
                     tmem_wait_st();
@@ -346,7 +373,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         // MMA issuer of tile t.  Ring cursors advance incrementally; descriptors differ only in their low word.
         // =====================================================================================================
         const int t = warp - kTcActWarps;
-        constexpr uint32_t id1 = tc_idesc(kTcChunk), id2 = tc_idesc(kTcN2);
+        constexpr uint32_t id1 = tc_idesc(kTcChunk), id2 = tc_idesc(kTcN2), id2h = tc_idesc_f16(kTcN2);
         const uint32_t wbase = smem_u32(wring);
         const uint64_t dB1 = tc_smem_desc(wbase, kTcChunk * 16, 128);
         const uint64_t dB2 = tc_smem_desc(wbase + 2 * kTcB1Floats * 4, kTcN2 * 16, 128);
@@ -389,16 +416,20 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     if (elect_one()) {
                         const int cc = c + b;
                         const uint32_t d2 = tb + kColD2 + 16 * ((cc / kTcGroup) & 1), dx = tb + kColD2X;
-                        const uint32_t ah = tb + kColD1 + kTcChunk * b, al = tb + kColA2L + kTcChunk * b;
+                        const uint32_t ah = tb + kColD1 + kTcChunk * b, al = tb + kColA2L + (kTcChunk / 2) * b;
                         const uint32_t gfirst = (cc & (kTcGroup - 1)) == 0 ? 0u : 1u, ffirst = cc == 0 ? 0u : 1u;
 #pragma unroll
-                        for (int s = 0; s < kTcKSteps; ++s) {   // one k-step = 8 hidden units = a 512-byte B tile
-                            mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : gfirst);
+                        for (int s = 0; s < kTcKSteps; ++s) {   // kind::tf32 k-step = 8 hidden units = a 512-byte B tile
+                            mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : gfirst);                      // h_hi W_hi
 #ifndef TCV_NO_L2X
-                            mma_tf32_ts(dx, al + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : ffirst);
-                            mma_tf32_ts(dx, ah + 8 * s, lo2 + s * 32 + ((kTcB2Floats * 4) >> 4), hi2, id2, 1u);
+                            mma_tf32_ts(dx, ah + 8 * s, lo2 + s * 32 + ((kTcB2Floats * 4) >> 4), hi2, id2, s > 0 ? 1u : ffirst);  // h_hi W_lo
 #endif
                         }
+#ifndef TCV_NO_L2X
+#pragma unroll
+                        for (int s = 0; s < kTcKSteps16; ++s)   // kind::f16 k-step = 16 hidden units = 8 columns of fp16 pairs
+                            mma_f16_ts(dx, al + 8 * s, lo2 + s * 32 + ((2 * kTcB2Floats * 4) >> 4), hi2, id2h, 1u);          // h_lo W_hi
+#endif
                         tc_commit(&bars->a2_free[t][b]);
                         tc_commit(&bars->w_free[s2]);
                         if (more) l1(b);  // the activation warps read D1[b] before they signalled a2_full[b]
