@@ -8,6 +8,7 @@ are evaluated by the CUDA engine (``nmma_b200.engine``), never on the CPU.
 from __future__ import annotations
 
 import os
+import sys
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -122,7 +123,7 @@ class LightCurveModelContainer:
         """``:249-267``: build the 50-point dL -> z table when distance (not redshift) is sampled."""
         for key in self.model_parameters:
             if key not in priors:
-                print(f"Parameter {key} not found in priors, might fail.")
+                print(f"Parameter {key} not found in priors, might fail.", file=sys.stderr)   # reference prints this to stdout
         if "redshift" not in priors and "luminosity_distance" in priors:
             dl = priors["luminosity_distance"]
             lo = getattr(dl, "minimum", None)
