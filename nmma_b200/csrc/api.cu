@@ -342,9 +342,43 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                 rec[3] = sg; rec[4] = 1.0 / sg; rec[5] = o_lsc[k];
                 float* rf = reinterpret_cast<float*>(rec + 6);
                 rf[0] = (float)h->o_t[k]; rf[1] = (float)h->o_m[k]; rf[2] = (float)(1.0 / sg); rf[3] = (float)o_lsc[k];
-                // plain detection: constant budget, no detection limit, finite sigma_obs (fp32 Gaussian term)
-                const int simple = (sy_mode[g] == 0 && h->g_lim[g] == INFINITY && std::isfinite(h->o_s[k])) ? 1 : 0;
-                std::memcpy(rec + 8, &simple, sizeof(int));
+                // observation class of the FAST back end (kernels.cuh: kObsGeneral / kObsSimple / kObsSampled)
+                const double lim = h->g_lim[g], tk = h->o_t[k];
+                const bool det = std::isfinite(h->o_s[k]) && std::isfinite(h->o_m[k]) && std::isfinite(tk);
+                int cls = kObsGeneral, i0 = -1, i1 = -1;
+                float wgt = 0.f;
+                if (det && sy_mode[g] == 0 && lim == INFINITY) {
+                    cls = kObsSimple;
+                } else if (det && h->o_m[k] <= lim && !std::isnan(lim) && lim > -INFINITY) {
+                    // the support test m <= limit does not depend on the point; m > limit stays on the exact path (-inf)
+                    if (sy_mode[g] == 0) {
+                        cls = kObsSampled;   // constant budget behind a finite detection limit
+                    } else if (sy_mode[g] == 1) {
+                        cls = kObsSampled; i0 = i1 = sy_off[g];
+                    } else if (sy_mode[g] == 2 && sy_nn[g] >= 2) {
+                        // np.interp(t, nodes, values) with 'constant' ends (em/utils.py:667-670): fixed bracket and weight
+                        const double* tn = &sy_t[sy_off[g]];
+                        const int nn = sy_nn[g];
+                        bool sorted = true;
+                        for (int i = 0; i + 1 < nn; ++i) sorted = sorted && tn[i + 1] > tn[i];
+                        if (sorted) {
+                            cls = kObsSampled;
+                            if (tk <= tn[0]) { i0 = i1 = sy_off[g]; }
+                            else if (tk >= tn[nn - 1]) { i0 = i1 = sy_off[g] + nn - 1; }
+                            else {
+                                int j = (int)(std::upper_bound(tn, tn + nn, tk) - tn) - 1;
+                                i0 = sy_off[g] + j; i1 = i0 + 1;
+                                wgt = (float)((tk - tn[j]) / (tn[j + 1] - tn[j]));
+                            }
+                        }
+                    }
+                }
+                int32_t* ri = reinterpret_cast<int32_t*>(rec + 8);
+                ri[0] = cls; ri[1] = i0;
+                ri[2] = i1; std::memcpy(&ri[3], &wgt, sizeof(float));
+                float* rg = reinterpret_cast<float*>(rec + 10);
+                rg[0] = (float)(h->o_s[k] * h->o_s[k]); rg[1] = (float)lim;
+                rg[2] = (float)sy_budget[g]; rg[3] = 0.f;
             }
         std::vector<int> f_goff(F + 1, 0), f_glist;
         bool direct = true;

@@ -302,8 +302,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 constexpr int kFusedThreads = 256;   // 8 warps, all consumers
 constexpr int kHC = 128;             // hidden units per weight chunk (8 KB at 16 floats per unit)
 constexpr int kWStages = 6;          // weight ring depth
-constexpr int kObsRec = 10;          // doubles per staged observation record: t, mag, sigma_obs, sigma, 1/sigma,
-                                     // log(sigma)+C | fp32 (t, mag, 1/sigma, log(sigma)+C) | int simple-detection flag, pad
+constexpr int kObsRec = 12;          // doubles per staged observation record: t, mag, sigma_obs, sigma, 1/sigma, log(sigma)+C
+                                     // | fp32 (t, mag, 1/sigma, log(sigma)+C) | int (class, node i0) | (int node i1, fp32 weight)
+                                     // | fp32 (sigma_obs^2, detection limit) | fp32 (budget, pad)     (api.cu: finalize)
+// observation classes of the FAST back end
+constexpr int kObsGeneral = 0;       // fp64 obs_term: upper limits, mag > limit, anything unusual
+constexpr int kObsSimple = 1;        // detection, constant budget, no detection limit: everything staged on the host
+constexpr int kObsSampled = 2;       // detection with sampled / time-interpolated sigma_sys and / or a finite detection limit
 
 __host__ __device__ constexpr int fused_rw(int D, int K) { return (D + 1 + K + 3) / 4 * 4; }
 __host__ __device__ inline size_t fused_bslot(int K, int T) {
@@ -354,10 +359,12 @@ __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, co
         for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
             const int g = cfg.f_glist[gi];
             const int k1 = cfg.g_off[g + 1];
+            int cur0 = -1, cur1 = -1;      // systematics nodes whose per-point values nv0 / nv1 are loaded
+            double nv0 = 0.0, nv1 = 0.0;
             for (int k = cfg.g_off[g]; k < k1; ++k) {
                 const double* rec = s_obs + k * kObsRec;
                 const float4 rf = *reinterpret_cast<const float4*>(rec + 6);  // (float)t, (float)mag, 1/sigma, log(sigma)+C
-                const int simple = *reinterpret_cast<const int*>(rec + 8);
+                const int2 cls = *reinterpret_cast<const int2*>(rec + 8);      // class, left systematics node
                 const double t = rec[0];
                 const float gq = fmaf(rf.x, ga, gb);
                 int j = __float2int_rd(gq);
@@ -392,12 +399,50 @@ __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, co
                     const float a0 = fmaf(d0, sc.x, mn.x), a1 = fmaf(d1, sc.y, mn.y);
                     mu = fmaf(wgt, a1 - a0, a0) + dmz;
                 }
-                if (simple) {
+                bool general = cls.x == kObsGeneral;
+                if (cls.x == kObsSimple) {
                     // truncnorm.logpdf with b = +inf = the plain Gaussian log-density; mu = +inf gives -inf here where
                     // SciPy gives NaN: both end as the sentinel (core/base.py:180-181)
                     const float xq = (rf.y - mu) * rf.z;
                     lsum += (double)fmaf(-0.5f * xq, xq, -rf.w);
-                } else {
+                } else if (cls.x == kObsSampled) {
+                    // sigma_sys at this observation time: the bracketing nodes and the weight are fixed per observation
+                    // (systematics.py:288-291 through np.interp with 'constant' ends); the node values are per point
+                    const int2 nd = *reinterpret_cast<const int2*>(rec + 9);     // right node, weight bits
+                    const float2 sl = *reinterpret_cast<const float2*>(rec + 10);  // sigma_obs^2, detection limit
+                    float ssys;
+                    if (cls.y < 0) {
+                        ssys = *reinterpret_cast<const float*>(rec + 11);          // constant budget
+                    } else {
+                        if (cls.y != cur0 || nd.x != cur1) {   // warp-uniform: all lanes walk the same observation list
+                            cur0 = cls.y; cur1 = nd.x;
+                            nv0 = eval_src(cfg.sy_src[cur0], row);
+                            nv1 = (cur1 == cur0) ? nv0 : eval_src(cfg.sy_src[cur1], row);
+                        }
+                        ssys = (float)fma((double)__int_as_float(nd.y), nv1 - nv0, nv0);
+                        general = !(isfinite(nv0) && isfinite(nv1));   // a dropped node changes the bracket: exact path
+                    }
+                    const float s2 = fmaf(ssys, ssys, sl.x);
+                    const float inv = rsqrtf(s2);
+                    const float xq = (rf.y - mu) * inv;
+                    float term = fmaf(-0.5f * xq, xq, -0.5f * logf(s2) - (float)NMMA_NORM_PDF_LOGC);
+                    if (sl.y < CUDART_INF_F) {   // truncation at the detection limit: - log Phi((lim - mu) / sigma)
+                        const float bq = (sl.y - mu) * inv;
+                        float mass = 0.f;                                                  // log Phi(bq); Phi(-8.3) < 2^-53
+                        if (bq > 0.f) {
+                            if (bq < 8.3f) mass = log1pf(-0.5f * erfcf(bq * 0.70710678f));
+                        } else if (bq > -12.f) {
+                            mass = logf(0.5f * erfcf(-bq * 0.70710678f));
+                        } else {   // log_ndtr's asymptotic series (scipy/special/_log_ndtr: -b^2/2 - log(-b) - log(2 pi)/2 + log(1 - 1/b^2 + 3/b^4))
+                            const float r2 = 1.0f / (bq * bq);
+                            mass = fmaf(-0.5f * bq, bq, -logf(-bq) - (float)NMMA_NORM_PDF_LOGC) + log1pf(r2 * (3.0f * r2 - 1.0f));
+                        }
+                        term -= mass;
+                    }
+                    general = general || !(s2 > 0.f) || !(s2 < CUDART_INF_F);
+                    if (!general) lsum += (double)term;
+                }
+                if (general) {
                     const double so = rec[2];
                     const double mud = (double)mu;
                     if (cfg.sy_mode[g] == 0 && isfinite(so)) lsum += obs_term_static_det(rec[1], mud, rec[3], rec[5], cfg.g_lim[g]);
