@@ -232,7 +232,11 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         // tensor-core operand tiles (tc_kernel.cuh): K-major, no swizzle, hi/lo split
         c.tc_nch = 0;
         c.tcpack = nullptr;
-        if (d + 1 <= 8 && K <= kTcN2) {
+        // the h_lo W_hi term runs on fp16 copies of W_hi / 2 (tc_kernel.cuh): weights outside the fp16 range keep the
+        // tensor-core path off (the FFMA kernel takes over)
+        bool w2_fp16_ok = true;
+        for (float w : h->W2) w2_fp16_ok = w2_fp16_ok && std::isfinite(w) && std::fabs(w) < 6.0e4f;
+        if (d + 1 <= 8 && K <= kTcN2 && w2_fp16_ok) {
             int nch = (H + kTcChunk - 1) / kTcChunk;
             nch = (nch + kTcGroup - 1) / kTcGroup * kTcGroup;  // whole layer-2 accumulation groups (and an even count)
             c.tc_nch = nch;

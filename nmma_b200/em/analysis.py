@@ -22,7 +22,7 @@ from typing import Optional
 
 import numpy as np
 
-from ..core.priors import PriorDict
+from ..core.priors import PriorDict, fixed_value, is_fixed_prior
 from ..samplers import equal_weight, nested_sample
 from . import io, utils
 from .em_likelihood import EMTransientLikelihood
@@ -65,6 +65,7 @@ def get_parser() -> argparse.ArgumentParser:
     p.add_argument("--batch", type=int, default=16384, help="candidate points per likelihood launch")
     p.add_argument("--seed", "--sampler-seed", dest="seed", type=int, default=42)
     p.add_argument("--nposterior", type=int, default=5000, help="equal-weight posterior samples to write")
+    p.add_argument("--max-calls", type=int, default=200_000_000, help="likelihood-evaluation budget of the sampler")
     return p
 
 
@@ -119,14 +120,15 @@ def analysis(args, svd_mag_model=None) -> dict:
         return np.asarray(loglike(transform(np.ascontiguousarray(u, dtype=np.float64))), dtype=float)
 
     t1 = time.time()
-    res = nested_sample(loglike_u, len(columns), nlive=args.nlive, batch=args.batch, dlogz=args.dlogz, seed=args.seed)
+    res = nested_sample(loglike_u, len(columns), nlive=args.nlive, batch=args.batch, dlogz=args.dlogz, seed=args.seed,
+                        max_calls=args.max_calls)
     t2 = time.time()
     idx = equal_weight(res, args.nposterior, seed=args.seed)
     theta = np.asarray(transform(np.ascontiguousarray(res["samples_u"][idx])), dtype=float)
     logl = np.asarray(res["log_likelihoods"])[idx]
     best = int(np.argmax(res["log_likelihoods"]))
     best_theta = np.asarray(transform(np.ascontiguousarray(res["samples_u"][best:best + 1])), dtype=float)[0]
-    fixed = {k: float(priors[k].peak) for k in priors.fixed_keys()} if hasattr(priors, "fixed_keys") else {}
+    fixed = {k: float(fixed_value(priors[k])) for k in priors if is_fixed_prior(priors[k])}
     posterior = {c: theta[:, i].tolist() for i, c in enumerate(columns)}
     posterior["log_likelihood"] = logl.tolist()
     result = {

@@ -38,16 +38,25 @@ def _ellipsoid(u: np.ndarray, enlarge: float):
     return mean, chol * np.sqrt(r2) * enlarge ** (1.0 / ndim)
 
 
-def _draw(rng, mean, axes, n):
+def _draw(rng, mean, axes, n, max_raw=1 << 22):
+    """About `n` points uniform in the ellipsoid intersected with the unit cube (the raw draw is enlarged by the
+    measured in-cube fraction, so a posterior on a prior edge still fills the likelihood batch)."""
     ndim = mean.size
-    z = rng.standard_normal((n, ndim))
-    z *= (rng.random(n) ** (1.0 / ndim) / np.linalg.norm(z, axis=1))[:, None]
-    x = mean + z @ axes.T
-    return x[np.all((x > 0.0) & (x < 1.0), axis=1)]
+    out, have, raw = [], 0, n
+    for _ in range(8):
+        z = rng.standard_normal((raw, ndim))
+        z *= (rng.random(raw) ** (1.0 / ndim) / np.linalg.norm(z, axis=1))[:, None]
+        x = mean + z @ axes.T
+        x = x[np.all((x > 0.0) & (x < 1.0), axis=1)]
+        out.append(x); have += x.shape[0]
+        if have >= n // 2:
+            break
+        raw = int(min(max_raw, max(n, (n - have) * raw / max(x.shape[0], 1) * 1.2)))
+    return np.concatenate(out)[:n]
 
 
 def nested_sample(loglike: Callable[[np.ndarray], np.ndarray], ndim: int, nlive: int = 512, batch: int = 8192,
-                  dlogz: float = 0.1, seed: int = 0, enlarge: float = 1.5, max_calls: int = 200_000_000,
+                  dlogz: float = 0.1, seed: int = 0, enlarge: float = 2.0, max_calls: int = 200_000_000,
                   floor: float = -1e300) -> Dict[str, object]:
     """Returns ``log_evidence``, ``log_evidence_err``, the dead + final live points in the unit cube (``samples_u``)
     with ``log_weights`` (normalised posterior weights) and ``log_likelihoods``, ``ncall`` and ``niter``.
@@ -86,7 +95,8 @@ def nested_sample(loglike: Callable[[np.ndarray], np.ndarray], ndim: int, nlive:
         cl[~(cl > floor)] = -np.inf
         ncall += cand.shape[0]
         worst = int(np.argmin(logl))
-        for c in range(cand.shape[0]):
+        # the threshold only rises: candidates at or below the current minimum can never be accepted
+        for c in np.nonzero(cl > logl[worst])[0]:
             lmin = logl[worst]
             if not cl[c] > lmin:
                 continue

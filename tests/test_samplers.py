@@ -38,10 +38,25 @@ def test_sentinel_rows_count_as_zero_likelihood():
     assert np.all(res["samples_u"][np.isfinite(res["log_likelihoods"]), 0] <= 0.5)
 
 
+def test_driver_parser_takes_the_reference_flags():
+    """Option names and dests of nmma/em/em_parsing.py that reach the kilonova likelihood."""
+    from nmma_b200.em import analysis
+    a = analysis.get_parser().parse_args(
+        ["--model", "Bu2019lm", "--svd-path", "svdmodels", "--interpolation-type", "tensorflow", "--outdir", "o",
+         "--label", "l", "--trigger-time", "57982.5285236896", "--data", "AT2017gfo.dat", "--prior", "Bu2019lm.prior",
+         "--tmin", "0.1", "--tmax", "14", "--dt", "0.5", "--error-budget", "1", "--nlive", "256", "--filters", "ps1::g,ps1::r",
+         "--detection-limit", "24.5", "--remove-nondetections", "--svd-mag-ncoeff", "10", "--data-tmax", "14"])
+    assert a.em_model == "Bu2019lm" and a.light_curve_data == "AT2017gfo.dat" and a.em_tmin == 0.1 and a.em_tmax == 14
+    assert a.em_tstep == 0.5 and a.em_error_budget == 1.0 and a.nlive == 256 and a.detection_limit == 24.5
+    b = analysis.get_parser().parse_args(["--kilonova-model", "Ka2017", "--label", "l", "--light-curve-data", "x",
+                                          "--prior", "p", "--kilonova-tmin", "0.2", "--em-tstep", "0.1", "--kilonova-error", "0.5"])
+    assert b.em_model == "Ka2017" and b.em_tmin == 0.2 and b.em_tstep == 0.1 and b.em_error_budget == 0.5
+
+
 @pytest.mark.gpu
 def test_lightcurve_analysis_driver(tmp_path):
     """Config 1 end to end on the device: AT2017gfo vs a Bu2019lm-shaped surrogate, nested sampling through the batched
-    likelihood; ln Z is checked against a brute-force prior sweep (2e8 Philox draws scored on the device)."""
+    likelihood; ln Z is checked against a brute-force prior sweep (1e8 Philox draws scored on the device)."""
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
@@ -52,10 +67,12 @@ def test_lightcurve_analysis_driver(tmp_path):
         blob = json.load(fh)
     data = {f: {k: np.array([np.inf if x == "inf" else x for x in v], float) for k, v in d.items()}
             for f, d in blob["data"].items()}
+    # a 3 mag error budget keeps the posterior broad enough for the brute-force sweep to have thousands of effective
+    # samples (a random-init surrogate does not fit AT2017gfo; with 1 mag the sweep's evidence is the noisier number)
     args = analysis.get_parser().parse_args(
         ["--model", "Bu2019lm", "--label", "at2017gfo", "--outdir", str(tmp_path), "--light-curve-data", "unused",
-         "--prior", "unused", "--trigger-time", str(syn.AT2017GFO_TRIGGER_MJD), "--data-tmax", "14", "--nlive", "1024",
-         "--em-error-budget", "1"])
+         "--prior", "unused", "--trigger-time", str(syn.AT2017GFO_TRIGGER_MJD), "--data-tmax", "14", "--nlive", "500",
+         "--em-error-budget", "3", "--batch", "65536", "--max-calls", "30000000", "--dlogz", "0.2"])
     args.light_curve_data = data                      # load_em_observations accepts the dict form
     args.prior = syn.bu2019lm_prior()
     core = syn.random_model("Bu2019lm", list(data), seed=0)
@@ -66,7 +83,7 @@ def test_lightcurve_analysis_driver(tmp_path):
 
     _, lik = analysis.analysis_setup(args, svd_mag_model=core)
     tot, n, best = -np.inf, 0, -np.inf
-    for blk in range(20):
+    for blk in range(10):
         out = lik.log_likelihood_sweep(10_000_000, seed=7, first_index=blk * 10_000_000)
         o = out.cpu().numpy() if hasattr(out, "cpu") else np.asarray(out)
         o = o[o > -1e300]
