@@ -463,6 +463,7 @@ int nmma_b200_destroy(nmma_b200_t* h) {
     cudaSetDevice(h->device);
     free_dev(h);
     if (h->coeff_scratch) cudaFree(h->coeff_scratch);
+    if (h->tc_parts) cudaFree(h->tc_parts);
     if (h->pr_dev) cudaFree(h->pr_dev);
     if (h->pr_tab_dev) cudaFree(h->pr_tab_dev);
     if (h->sweep_scratch) cudaFree(h->sweep_scratch);
@@ -812,6 +813,7 @@ int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     else if (k == "pipeline_blocks") { if (value < 1 || value > 64) return fail(h, NMMA_B200_ERR_ARG, "pipeline_blocks must be 1..64"); h->opt_pipeline = (int)value; }
     else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }
     else if (k == "no_fast_backend") h->opt_no_fast = value ? 1 : 0;
+    else if (k == "no_filter_split") h->opt_no_fsplit = value ? 1 : 0;
     else if (k == "points_per_thread") { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, NMMA_B200_ERR_ARG, "points_per_thread must be 0 (auto), 1, 2 or 4"); h->opt_pt = (int)value; }
     else return fail(h, NMMA_B200_ERR_ARG, "unknown option '%s'", key);
     return NMMA_B200_OK;

@@ -57,6 +57,8 @@ struct nmma_b200_handle {
     bool tc_supported = false;
     bool hy_supported = false;
     double* coeff_scratch = nullptr;
+    double* tc_parts = nullptr;       // per-part sums of a filter-split tensor-core launch (launch_tc.cu)
+    size_t tc_parts_cap = 0;
     size_t coeff_cap = 0;
     double* stage_in_dev = nullptr;
     double* stage_out_dev = nullptr;
@@ -70,10 +72,12 @@ struct nmma_b200_handle {
     // ---- knobs / counters ----
     int opt_path = 0;
     long long opt_fused_min = 2048;
-    long long opt_tc_min = 32768;     // tensor-core path from one wave of 148 CTAs x 256 points up (set_option "tc_min_points")
+    long long opt_tc_min = 48;        // tensor-core path: with the filters of a super-tile split over CTAs (launch_tc.cu) a call takes
+                                      // ~40 us up to 4096 points, the two-stage kernels ~20 us + 0.6 us per point (tools/latency.py)
     long long opt_hy_min = -1;        // hybrid (FFMA layer 1 + tcgen05 layer 2) kernel: opt-in (slower than the TC kernel); < 0 = never automatic
     int opt_max_ctas = 0;
     int opt_no_fast = 0;
+    int opt_no_fsplit = 0;            // set_option "no_filter_split": keep one CTA per super-tile
     int last_ctas_per_sm = 0;
     int opt_pt = 0;
     long long launches = 0;

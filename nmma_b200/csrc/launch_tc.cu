@@ -7,19 +7,49 @@
 namespace nmma {
 
 namespace {
+// Adds the per-part sums of a filter-split launch in part order (deterministic); any failed part -> sentinel.
+__global__ void combine_parts_kernel(const double* __restrict__ parts, int fsplit, long long N, double* __restrict__ out) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double s = 0.0;
+    for (int p = 0; p < fsplit; ++p) s += parts[n * fsplit + p];
+    out[n] = isfinite(s) ? s : NMMA_SENTINEL;
+}
+
 template <bool FAST>
 int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
     constexpr int K = 10;
-    auto kern = fused_tc_logl_kernel<K, FAST>;
     const size_t smem = tc_smem_bytes(K, h->T, h->cfg.S, h->cfg.nobs);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, FAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, FAST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long super = (long long)kTcTile * kTcTiles;
     const long long nsuper = (N + super - 1) / super;
     long long grid = h->sm_count;  // one CTA per SM: each CTA owns all 512 TMEM columns of its SM
     if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
-    grid = std::max<long long>(1, std::min(grid, nsuper));
-    kern<<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, out);
+    // small batches: a 256-point super-tile takes ~205 us on one SM whatever N is, so when the super-tiles leave SMs idle
+    // the filters of each are spread over several CTAs (per-part sums, combined in a fixed order)
+    int fsplit = 1;
+    if (!h->opt_no_fsplit && nsuper * 2 <= grid) fsplit = (int)std::min<long long>(h->F, grid / nsuper);
+    double* dst = out;
+    if (fsplit > 1) {
+        const size_t need = (size_t)N * fsplit;
+        if (need > h->tc_parts_cap) {
+            if (h->tc_parts) cudaFree(h->tc_parts);
+            h->tc_parts = nullptr; h->tc_parts_cap = 0;
+            CU(cudaMalloc((void**)&h->tc_parts, need * sizeof(double)));
+            h->tc_parts_cap = need;
+        }
+        dst = h->tc_parts;
+    }
+    grid = std::max<long long>(1, std::min(grid, nsuper * fsplit));
+    if (fsplit > 1) fused_tc_logl_kernel<K, FAST, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, dst, fsplit);
+    else fused_tc_logl_kernel<K, FAST, false><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, dst, 1);
     CU(cudaGetLastError());
+    if (fsplit > 1) {
+        combine_parts_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h->tc_parts, fsplit, N, out);
+        CU(cudaGetLastError());
+        h->launches += 1;
+    }
     h->launches += 1;
     h->last_ctas_per_sm = 1;
     return NMMA_B200_OK;

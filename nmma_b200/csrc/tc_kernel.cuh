@@ -203,9 +203,13 @@ struct TcBars {
     uint32_t tmem_base;
 };
 
-template <int K, bool FAST>
+template <int K, bool FAST, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ out) {
+fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ out, int fsplit_arg) {
+    const int fsplit = SPLIT ? fsplit_arg : 1;   // SPLIT = false: the throughput instantiation, index arithmetic folds away
+    // Work item = (256-point super-tile, filter part): with fsplit > 1 (small batches, launch_tc.cu) the filters of one
+    // super-tile are spread over fsplit CTAs and `out` receives the per-part sums [N][fsplit] (NaN = failed) that
+    // combine_parts_kernel adds in a fixed order; with fsplit == 1 `out` is the final log-likelihood.
     static_assert(K <= kTcN2, "n_coeff must fit the N=16 layer-2 MMA");
     extern __shared__ __align__(128) unsigned char smem[];
     const size_t wbytes = (size_t)kTcStages * kTcChunkBytes;
@@ -223,8 +227,11 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int F = cfg.F, NCH = cfg.tc_nch;
     constexpr int SUPER = kTcTile * kTcTiles;
-    const long long nsuper = (N + SUPER - 1) / SUPER;
+    const long long nsuper = ((N + SUPER - 1) / SUPER) * fsplit;   // work items
     const long long my_super = (nsuper > blockIdx.x) ? (nsuper - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // filters [f0, f1) of work item w: part p = w % fsplit takes p F / fsplit .. (p + 1) F / fsplit
+#define TC_PART_F0(w) (SPLIT ? (int)(((w) % fsplit) * F / fsplit) : 0)
+#define TC_PART_F1(w) (SPLIT ? (int)(((w) % fsplit + 1) * F / fsplit) : F)
     const uint32_t half = (uint32_t)NCH >> 1;  // NCH is even: TMEM buffer = c & 1, its use count = vseq * half + (c >> 1)
 
     if (tid == 0) {
@@ -259,10 +266,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(256 * t);
         uint32_t vseq = 0;  // (super-tile, filter) sequence number of this CTA
         for (long long it = 0; it < my_super; ++it) {
-            const long long sup = blockIdx.x + it * gridDim.x;
-            const long long n = sup * SUPER + (long long)t * kTcTile + pidx;
+            const long long item = blockIdx.x + it * gridDim.x;
+            const long long n = (item / fsplit) * SUPER + (long long)t * kTcTile + pidx;
             const double* row = pts + (n < N ? n : 0) * cfg.P;
-            for (int f = 0; f < F; ++f, ++vseq) {
+            for (int f = TC_PART_F0(item), f1 = TC_PART_F1(item); f < f1; ++f, ++vseq) {
                 // ---- layer-1 A operand: [x_hi, 1, 0.. | x_lo, 0, 0..] (fp64 scaling, fp32 cast like Keras) ----
                 bool okx = true;
                 {
@@ -394,7 +401,12 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             tc_commit(&bars->d1_full[t][b]);
         };
         uint32_t vseq = 0;
-        const long long total_v = my_super * F;
+        long long total_v = my_super * F;
+        if constexpr (SPLIT) {
+            total_v = 0;
+            for (long long it = 0; it < my_super; ++it)
+                total_v += TC_PART_F1(blockIdx.x + it * gridDim.x) - TC_PART_F0(blockIdx.x + it * gridDim.x);
+        }
         for (long long vv = 0; vv < total_v; ++vv, ++vseq) {
             mbar_wait(&bars->a1_full[t], vseq & 1);
 #pragma unroll
@@ -445,8 +457,14 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         // TMA producer
         // =====================================================================================================
         uint32_t st = 0, ph = 0, vseq = 0;
-        int f = 0;
-        const long long total_v = my_super * F;
+        long long total_v = my_super * F;
+        if constexpr (SPLIT) {
+            total_v = 0;
+            for (long long it = 0; it < my_super; ++it)
+                total_v += TC_PART_F1(blockIdx.x + it * gridDim.x) - TC_PART_F0(blockIdx.x + it * gridDim.x);
+        }
+        long long item = blockIdx.x;
+        int f = TC_PART_F0(item), f1 = TC_PART_F1(item);
         for (long long vv = 0; vv < total_v; ++vv, ++vseq) {
             const int slot = (int)(vseq & 1);
             mbar_wait(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
@@ -470,7 +488,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 __syncwarp();
                 if (++st == kTcStages) { st = 0; ph ^= 1; }
             }
-            if (++f == F) f = 0;
+            if (++f == f1) {   // next work item of this CTA
+                item += gridDim.x;
+                f = TC_PART_F0(item); f1 = TC_PART_F1(item);
+            }
         }
       }
     } else {
@@ -481,14 +502,14 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         const int pidx = ((warp - kTcBackWarp0) & 3) * 32 + lane;
         uint32_t vseq = 0;
         for (long long it = 0; it < my_super; ++it) {
-            const long long sup = blockIdx.x + it * gridDim.x;
-            const long long n = sup * SUPER + (long long)t * kTcTile + pidx;
+            const long long item = blockIdx.x + it * gridDim.x;
+            const long long n = (item / fsplit) * SUPER + (long long)t * kTcTile + pidx;
             const bool live = n < N;
             const double* row = pts + (live ? n : 0) * cfg.P;
             const PointScal ps = point_setup(cfg, row);
             bool ok = !ps.bad && !cfg.static_fail;
             double logl = 0.0;
-            for (int f = 0; f < F; ++f, ++vseq) {
+            for (int f = TC_PART_F0(item), f1 = TC_PART_F1(item); f < f1; ++f, ++vseq) {
                 const int slot = (int)(vseq & 1);
                 const uint32_t par = (vseq >> 1) & 1;
                 mbar_wait(&bars->c_full[t][slot], par);
@@ -521,12 +542,18 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->b_free[slot]);
             }
-            if (live) out[n] = (ok && isfinite(logl)) ? logl : NMMA_SENTINEL;
+            if (live) {
+                const bool good = ok && isfinite(logl);
+                if (fsplit == 1) out[n] = good ? logl : NMMA_SENTINEL;
+                else out[n * fsplit + item % fsplit] = good ? logl : CUDART_NAN;
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 11) tmem_dealloc(tmem, 512);
+#undef TC_PART_F0
+#undef TC_PART_F1
 }
 
 }  // namespace nmma
