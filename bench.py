@@ -379,8 +379,7 @@ def gpu_arm(args):
                         "frac_of_nominal": achieved / 74.4}
         roofline.update({"ffma_peak_measured": ffma, "algorithmic_flop_per_eval": flop, "kernel_ms_per_launch": kern_ms,
                          "hbm": hbm, "traffic": traffic})
-        kname = {1: "fused_mlp_logl_kernel (FFMA)", 2: "two_stage", 3: "fused_tc_logl_kernel (tcgen05 3xTF32)",
-                 4: "fused_hy_logl_kernel (FFMA layer 1 + tcgen05 layer 2)"}.get(last_path, "?")
+        kname = {1: "fused_mlp_logl_kernel (FFMA)", 2: "two_stage", 3: "fused_tc_logl_kernel (tcgen05 3xTF32)"}.get(last_path, "?")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,

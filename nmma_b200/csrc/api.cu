@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "handle.h"
-#include "hy_kernel.cuh"  // layout constants of the throughput kernels (weight packs are built here)
+#include "tc_kernel.cuh"  // layout constants of the tensor-core kernel (its weight pack is built here)
 
 using namespace nmma;
 
@@ -264,31 +264,6 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                 }
             if (int rc = upload(h, tp, &c.tcpack)) return rc;
         }
-        // hybrid kernel operands (hy_kernel.cuh): per 64-hidden group [W1 hidden-pair rows | W2 hi tiles | W2 lo tiles]
-        c.hy_ngrp = 0;
-        c.hypack = nullptr;
-        if (hy_has(d, K)) {
-            const int per = kHyGroup * kHyChunk;
-            const int ngrp = (H + per - 1) / per;
-            const int slot = hy_slot_floats(d), w1f = hy_w1_floats(d);
-            c.hy_ngrp = ngrp;
-            std::vector<float> hp((size_t)F * ngrp * slot, 0.f);
-            for (int f = 0; f < F; ++f)
-                for (int j = 0; j < H; ++j) {
-                    float* gp = &hp[((size_t)f * ngrp + j / per) * slot];
-                    const int jj = j % per, ch = jj / kHyChunk, n = jj % kHyChunk;
-                    // chunk ch: 4 hidden pairs, pair row = [b, b', w0, w0', ..., w(d-1), w(d-1)']
-                    float* wr = gp + ch * kHyChunk * (d + 1) + (n / 2) * 2 * (d + 1) + (n & 1);
-                    wr[0] = h->b1[(size_t)f * H + j];
-                    for (int i = 0; i < d; ++i) wr[2 + 2 * i] = h->W1[((size_t)f * d + i) * H + j];
-                    for (int o = 0; o < K; ++o) {
-                        const float w = h->W2[((size_t)f * H + j) * K + o];
-                        tf32_split(w, &gp[w1f + ch * 128 + tc_b_index(kTcN2, o, n)],
-                                   &gp[w1f + kHyB2Floats + ch * 128 + tc_b_index(kTcN2, o, n)]);
-                    }
-                }
-            if (int rc = upload(h, hp, &c.hypack)) return rc;
-        }
     } else {
         c.Ntr = h->Ntr;
         // GP inputs are scaled with filter 0's param_mins/maxs: training shares them (em/training.py:216-230)
@@ -313,7 +288,6 @@ int finalize(nmma_b200_t* h, bool need_obs) {
     // ---- observations + systematics ----
     h->fused_supported = false;
     h->tc_supported = false;
-    h->hy_supported = false;
     if (h->have_obs) {
         const int G = h->G;
         const int nobs = h->g_off[G];
@@ -415,8 +389,6 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                              fused_smem_bytes(d, K, T, c.S, nobs) <= 227 * 1024;
         h->tc_supported = (h->kind == 0) && direct && K == 10 && c.tc_nch > 0 &&
                           tc_smem_bytes(K, T, c.S, nobs) <= 227 * 1024;
-        h->hy_supported = (h->kind == 0) && direct && hy_has(d, K) && c.hy_ngrp > 0 &&
-                          hy_smem_bytes(d, K, T, c.S, nobs) <= 227 * 1024;
     }
     h->dirty = false;
     return NMMA_B200_OK;
@@ -650,15 +622,11 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused kernel unavailable for this configuration (GP path, averaged filters, or d/K not instantiated)");
     if (path == 3 && !h->tc_supported)
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "tensor-core kernel unavailable for this configuration (GP path, averaged filters, d > 7 or n_coeff != 10)");
-    if (path == 4 && !h->hy_supported)
-        return fail(h, NMMA_B200_ERR_UNSUPPORTED, "hybrid kernel unavailable for this configuration (GP path, averaged filters, d not in {3,4,7} or n_coeff != 10)");
     if (path == 0) {
-        if (h->hy_supported && h->opt_hy_min >= 0 && N >= h->opt_hy_min) path = 4;
-        else if (h->tc_supported && N >= h->opt_tc_min) path = 3;
+        if (h->tc_supported && N >= h->opt_tc_min) path = 3;
         else path = (h->fused_supported && N >= h->opt_fused_min) ? 1 : 2;
     }
     h->last_path = path;
-    if (path == 4) return launch_hy(h, points_dev, N, out_dev, st);
     if (path == 3) return launch_tc(h, points_dev, N, out_dev, st);
     if (path == 1) return launch_fused(h, points_dev, N, out_dev, st);
     const size_t FK = (size_t)h->F * h->K;
@@ -805,10 +773,9 @@ int nmma_b200_mags(nmma_b200_t* h, const double* points_dev, int64_t N, int appa
 int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     if (!h || !key) return NMMA_B200_ERR_ARG;
     const std::string k(key);
-    if (k == "path") { if (value < 0 || value > 4) return fail(h, NMMA_B200_ERR_ARG, "path must be 0 .. 4"); h->opt_path = (int)value; }
+    if (k == "path") { if (value < 0 || value > 3) return fail(h, NMMA_B200_ERR_ARG, "path must be 0 (auto), 1 (fused FFMA), 2 (two-stage) or 3 (tensor core)"); h->opt_path = (int)value; }
     else if (k == "fused_min_points") h->opt_fused_min = value;
     else if (k == "tc_min_points") h->opt_tc_min = value;
-    else if (k == "hy_min_points") h->opt_hy_min = value;
     else if (k == "max_ctas") h->opt_max_ctas = (int)value;
     else if (k == "pipeline_blocks") { if (value < 1 || value > 64) return fail(h, NMMA_B200_ERR_ARG, "pipeline_blocks must be 1..64"); h->opt_pipeline = (int)value; }
     else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }
@@ -827,7 +794,6 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
     else if (k == "sm_count") *value = h->sm_count;
     else if (k == "ctas_per_sm") *value = h->last_ctas_per_sm;
     else if (k == "fused_supported") { if (int rc = finalize(h, true)) return rc; *value = h->fused_supported ? 1 : 0; }
-    else if (k == "hy_supported") { if (int rc = finalize(h, true)) return rc; *value = h->hy_supported ? 1 : 0; }
     else if (k == "tc_supported") { if (int rc = finalize(h, true)) return rc; *value = h->tc_supported ? 1 : 0; }
     else if (k == "algorithmic_flop_per_eval") {
         // F * [2 H (d + K) + 2 T K] (MLP) or Ntr*3d + F*K*Ntr*8 + F*2*T*K (GP)

@@ -39,9 +39,6 @@ struct DevCfg {
     // tensor-core front end: per (filter, 48-hidden chunk) kTcChunkFloats = B1hi | B1lo | B2hi | B2lo operand tiles
     const float* tcpack;  // F*tc_nch*kTcChunkFloats
     int tc_nch;           // chunks per filter (even)
-    // hybrid front end (hy_kernel.cuh): per (filter, 64-hidden group) [W1/b1 hidden-pair rows | W2 hi tiles | W2 lo tiles]
-    const float* hypack;
-    int hy_ngrp;          // groups per filter
     // GP front end
     const double* gpX;    // Ntr*d
     const double* gpA;    // F*K*Ntr  constant_value * alpha_

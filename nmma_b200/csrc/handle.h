@@ -1,5 +1,5 @@
 // Host-side state of one engine handle and the launcher entry points shared by the translation units of
-// libnmma_b200.so (api.cu: C ABI, tables, two-stage kernels; launch_fused.cu / launch_tc.cu / launch_hy.cu: one
+// libnmma_b200.so (api.cu: C ABI, tables, two-stage kernels; launch_fused.cu / launch_tc.cu: one
 // throughput kernel family each, so that they compile in parallel).
 #pragma once
 #include "../../include/nmma_b200.h"
@@ -55,7 +55,6 @@ struct nmma_b200_handle {
     nmma::DevCfg cfg{};
     bool fused_supported = false;
     bool tc_supported = false;
-    bool hy_supported = false;
     double* coeff_scratch = nullptr;
     double* tc_parts = nullptr;       // per-part sums of a filter-split tensor-core launch (launch_tc.cu)
     size_t tc_parts_cap = 0;
@@ -74,7 +73,6 @@ struct nmma_b200_handle {
     long long opt_fused_min = 2048;
     long long opt_tc_min = 48;        // tensor-core path: with the filters of a super-tile split over CTAs (launch_tc.cu) a call takes
                                       // ~40 us up to 4096 points, the two-stage kernels ~20 us + 0.6 us per point (tools/latency.py)
-    long long opt_hy_min = -1;        // hybrid (FFMA layer 1 + tcgen05 layer 2) kernel: opt-in (slower than the TC kernel); < 0 = never automatic
     int opt_max_ctas = 0;
     int opt_no_fast = 0;
     int opt_no_fsplit = 0;            // set_option "no_filter_split": keep one CTA per super-tile
@@ -92,8 +90,6 @@ int fail(nmma_b200_t* h, int code, const char* fmt, ...);
 int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
 bool fused_has(int d, int K);
 int launch_tc(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
-int launch_hy(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
-bool hy_has(int d, int K);
 }  // namespace nmma
 
 #define CU(call)                                                                          \
