@@ -40,7 +40,10 @@ def _paths(lik, pts, cols):
         eng.set_option("points_per_thread", 0)
     if eng.get_info("tc_supported"):
         eng.set_option("path", 3)                             # tcgen05 3xTF32 kernel
-        out["fused_tc"] = eng.logl_host(pts)
+        out["fused_tc"] = eng.logl_host(pts)                  # small batches: filters split over CTAs (launch_tc.cu)
+        eng.set_option("no_filter_split", 1)
+        out["fused_tc_unsplit"] = eng.logl_host(pts)          # the throughput instantiation on the same points
+        eng.set_option("no_filter_split", 0)
         eng.set_option("no_fast_backend", 1)
         out["fused_tc_generic"] = eng.logl_host(pts)
         eng.set_option("no_fast_backend", 0)
