@@ -80,12 +80,60 @@ coeff_mlp_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, 
 // ---------------------------------------------------------------------------------------------
 constexpr int kGpThreads = 256;
 constexpr int kGpPts = 4;  // points per CTA (alpha vectors are re-used across them)
+constexpr int kGpTab = 256;   // entries of each pow table (kGpThreads threads fill them)
+
+// base^-alpha for base >= 1, alpha > 0 in ~20 fp64 instructions instead of the ~85 of exp(-alpha * log(base)): the GP front
+// end is fp64-issue bound (F K Ntr kernel values per evaluation, profiles/r01_config_rates.txt).  log2: base = 2^e m,
+// m = c_i (1 + u) with c_i the centre of the i-th of 256 mantissa cells (|u| < 2^-9), degree-6 series of log(1+u);
+// exp2: 256 x t = k + r, table 2^(j/256), degree-5 series.  Max relative error 5e-15 against a 40-digit reference, the
+// same as exp(-alpha log(base)) with the CUDA math library (3e-15); tools/tc_numerics.py-style check in tests.
+struct RqTabs {
+    double inv_c[kGpTab];   // 1 / c_i
+    double l2c[kGpTab];     // log2(c_i)
+    double e2[kGpTab];      // 2^(j / 256)
+};
+__device__ __forceinline__ void rq_tabs_fill(RqTabs& tb, int tid) {
+    if (tid < kGpTab) {
+        const double c = 1.0 + ((double)tid + 0.5) / kGpTab;
+        tb.inv_c[tid] = 1.0 / c;
+        tb.l2c[tid] = log2(c);
+        tb.e2[tid] = exp2((double)tid / kGpTab);
+    }
+}
+__device__ __forceinline__ double rq_pow(double base, double alpha, const RqTabs& tb) {
+    const int hi = __double2hiint(base), lo = __double2loint(base);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    const int i = (hi >> 12) & (kGpTab - 1);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double u = fma(m, tb.inv_c[i], -1.0);
+    double p = -1.0 / 6.0;
+    p = fma(p, u, 0.2);
+    p = fma(p, u, -0.25);
+    p = fma(p, u, 1.0 / 3.0);
+    p = fma(p, u, -0.5);
+    p = fma(p, u, 1.0);
+    const double lg2 = fma(p * u, 1.4426950408889634, (double)e + tb.l2c[i]);
+    const double t2 = -alpha * lg2;
+    if (!(t2 > -1020.0)) return (t2 != t2) ? t2 : 0.0;
+    const int k = __double2int_rn(t2 * kGpTab);
+    const double x = fma(-(double)k, 1.0 / kGpTab, t2) * 0.6931471805599453;
+    double q = 1.0 / 120.0;
+    q = fma(q, x, 1.0 / 24.0);
+    q = fma(q, x, 1.0 / 6.0);
+    q = fma(q, x, 0.5);
+    q = fma(q, x, 1.0);
+    q = fma(q, x, 1.0);
+    const double v = tb.e2[k & (kGpTab - 1)] * q;                       // in [0.99, 2.01)
+    return __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));   // * 2^floor(k / 256), k <= 0
+}
 
 __global__ void __launch_bounds__(kGpThreads)
 coeff_gp_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ coeff) {
     extern __shared__ double r2s[];  // kGpPts * Ntr
+    __shared__ RqTabs tabs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = cfg.d, K = cfg.K, Ntr = cfg.Ntr, F = cfg.F;
+    rq_tabs_fill(tabs, tid);
     const long long ntiles = (N + kGpPts - 1) / kGpPts;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long n0 = tile * kGpPts;
@@ -130,7 +178,7 @@ coeff_gp_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, d
 #pragma unroll
                 for (int p = 0; p < kGpPts; ++p) {
                     const double base = 1.0 + r2s[p * Ntr + t] * q;  // 1 + dists / (2 alpha)
-                    const double kv = exp(-ra * log(base));          // base ** -alpha
+                    const double kv = rq_pow(base, ra, tabs);        // base ** -alpha
                     acc[p] = fma(kv, a, acc[p]);
                 }
             }
