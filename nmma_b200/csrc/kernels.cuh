@@ -9,7 +9,8 @@
 //   backend_mags_kernel back end for generate_lightcurve / gen_detector_lc parity
 //   fused_mlp_logl_kernel  throughput mapping: persistent CTAs, thread-per-point register
 //                      tiling, per-filter weights streamed through a TMA (cp.async.bulk) +
-//                      mbarrier shared-memory ring, fp32 FFMA MLP, fp64 back end, one store/point
+//                      mbarrier shared-memory ring, fp32 FFMA MLP, back end with fp64 accumulation
+//                      (fused_filter_logl), one store/point
 #pragma once
 #include "backend.cuh"
 

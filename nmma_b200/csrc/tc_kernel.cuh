@@ -374,8 +374,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 if (lane == 0) mbar_arrive(&bars->c_full[t][slot]);
             }
         }
-    } else if (warp < kTcBackWarp0) {
-      if (warp < kTcActWarps + kTcTiles) {
+    } else if (warp < kTcActWarps + kTcTiles) {
         // =====================================================================================================
         // MMA issuer of tile t.  Ring cursors advance incrementally; descriptors differ only in their low word.
         // =====================================================================================================
@@ -452,7 +451,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 }
             }
         }
-      } else if (warp == 10) {
+    } else if (warp == 10) {
         // =====================================================================================================
         // TMA producer
         // =====================================================================================================
@@ -493,10 +492,9 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 f = TC_PART_F0(item); f1 = TC_PART_F1(item);
             }
         }
-      }
-    } else {
+    } else if (warp >= kTcBackWarp0) {
         // =====================================================================================================
-        // back-end warps: fp64 likelihood of filter f while the tensor cores work on filter f + 1
+        // back-end warps: likelihood of filter f (kernels.cuh: fused_filter_logl) while the tensor cores work on filter f + 1
         // =====================================================================================================
         const int t = (warp - kTcBackWarp0) >> 2;
         const int pidx = ((warp - kTcBackWarp0) & 3) * 32 + lane;
