@@ -87,7 +87,7 @@ constexpr int kGpTab = 256;   // entries of each pow table (kGpThreads threads f
 // end is fp64-issue bound (F K Ntr kernel values per evaluation, profiles/r01_config_rates.txt).  log2: base = 2^e m,
 // m = c_i (1 + u) with c_i the centre of the i-th of 256 mantissa cells (|u| < 2^-9), degree-6 series of log(1+u);
 // exp2: 256 x t = k + r, table 2^(j/256), degree-5 series.  Max relative error 5e-15 against a 40-digit reference, the
-// same as exp(-alpha log(base)) with the CUDA math library (3e-15); tools/tc_numerics.py-style check in tests.
+// same as exp(-alpha log(base)) with the CUDA math library (3e-15); restated and checked in tests/test_rq_pow.py.
 struct RqTabs {
     double inv_c[kGpTab];   // 1 / c_i
     double l2c[kGpTab];     // log2(c_i)

@@ -15,7 +15,7 @@ from typing import Callable, Dict
 
 import numpy as np
 
-__all__ = ["nested_sample"]
+__all__ = ["nested_sample", "equal_weight"]
 
 
 def _ellipsoid(u: np.ndarray, enlarge: float):
