@@ -175,7 +175,9 @@ def reference_arm(args):
     probe, _ = wl["priors"].sample_array(arm.cores * 40, rng, cols)
     _, dt = arm.run(probe)
     rate = len(probe) / dt
-    per_step = int(max(arm.cores * 40, min(rate * 4.0, 200000)))   # ~4 s of CPU work per step
+    # bounded sample: ~4 s of CPU work per step, shrunk so that steps + warm-up stay within ~2 minutes whatever K is
+    sec_per_step = min(4.0, max(0.2, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = int(max(arm.cores * 40, min(rate * sec_per_step, 200000)))
     pts, _ = wl["priors"].sample_array(per_step, rng, cols)
     for _ in range(args.warmup):
         arm.run(pts)
