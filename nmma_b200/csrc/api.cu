@@ -657,6 +657,8 @@ static bool is_device_mem(const void* p) {
     return a.type == cudaMemoryTypeDevice;
 }
 
+constexpr int64_t kZeroCopyMax = 256;   // rows up to which nmma_b200_logl_host skips the staging copies
+
 int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host) {
     if (!h) return NMMA_B200_ERR_ARG;
     if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "logl_host: N < 0");
@@ -696,7 +698,15 @@ int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, do
     long long rows = (N + nblk - 1) / nblk;
     if (nblk > 1) rows = (rows + wave - 1) / wave * wave;
     nblk = (N + rows - 1) / rows;
-    if (nblk == 1) {
+    if (nblk == 1 && N <= kZeroCopyMax && !out_dev && h->opt_zero_copy) {
+        // latency path (one point per call from bilby / pymultinest, small live-point batches): the kernels read the rows
+        // from and write the results to page-locked host memory directly (unified addressing), which removes two copy
+        // calls and their DMA round trips from a call whose kernels take ~40 us (tools/latency_breakdown.py)
+        const double* src = points_host;
+        if (!in_pinned) { std::memcpy(h->stage_in_host, points_host, nin * sizeof(double)); src = h->stage_in_host; }
+        if (int rc = nmma_b200_logl(h, src, N, dst, h->own_stream)) return rc;
+        CU(cudaStreamSynchronize(h->own_stream));
+    } else if (nblk == 1) {
         const double* src = points_host;
         if (!in_pinned) { std::memcpy(h->stage_in_host, points_host, nin * sizeof(double)); src = h->stage_in_host; }
         CU(cudaMemcpyAsync(h->stage_in_dev, src, nin * sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
@@ -781,6 +791,7 @@ int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }
     else if (k == "no_fast_backend") h->opt_no_fast = value ? 1 : 0;
     else if (k == "no_filter_split") h->opt_no_fsplit = value ? 1 : 0;
+    else if (k == "zero_copy") h->opt_zero_copy = value ? 1 : 0;
     else if (k == "points_per_thread") { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, NMMA_B200_ERR_ARG, "points_per_thread must be 0 (auto), 1, 2 or 4"); h->opt_pt = (int)value; }
     else return fail(h, NMMA_B200_ERR_ARG, "unknown option '%s'", key);
     return NMMA_B200_OK;

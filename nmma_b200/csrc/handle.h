@@ -71,10 +71,12 @@ struct nmma_b200_handle {
     // ---- knobs / counters ----
     int opt_path = 0;
     long long opt_fused_min = 2048;
-    long long opt_tc_min = 48;        // tensor-core path: with the filters of a super-tile split over CTAs (launch_tc.cu) a call takes
-                                      // ~40 us up to 4096 points, the two-stage kernels ~20 us + 0.6 us per point (tools/latency.py)
+    long long opt_tc_min = 1;         // tensor-core path from the first point: with the filters of a super-tile split over CTAs
+                                      // (launch_tc.cu) one call takes 39 us at N = 1 and 40-46 us up to 4096 points, the two-stage
+                                      // kernels 47 us + 0.6 us per point (tools/latency_breakdown.py, tools/latency.py)
     int opt_max_ctas = 0;
     int opt_no_fast = 0;
+    int opt_zero_copy = 1;            // set_option "zero_copy": small host batches are read / written in place (pinned memory)
     int opt_no_fsplit = 0;            // set_option "no_filter_split": keep one CTA per super-tile
     int last_ctas_per_sm = 0;
     int opt_pt = 0;
