@@ -14,7 +14,10 @@
  * arrays are borrowed for the duration of the call only.  Device pointers
  * passed in stay caller-owned and must live on the handle's device.  Work is
  * enqueued on the caller-supplied cudaStream_t (passed as void*).  A handle is
- * not thread-safe; distinct handles are independent.
+ * not thread-safe and owns per-handle scratch buffers: keep ONE stream in flight per
+ * handle (calls on a second stream must wait for the first to finish); distinct
+ * handles are independent.  A device-side wait that exceeds 8 s (which only a bug
+ * could cause) traps: the call then fails with NMMA_B200_ERR_CUDA instead of hanging.
  *
  * Layout symbols: F model filters, d model inputs, K SVD coefficients kept
  * (n_coeff), T model time-grid nodes, S sample-grid nodes, H hidden units,
@@ -73,6 +76,14 @@ enum {
     NMMA_B200_SYS_INTERP = 2  /* from_interpolated_params: time nodes, 'constant' extrapolation */
 };
 
+/* Extinction law of gen_detector_lc, nmma/em/model.py:201,323-342. */
+enum {
+    NMMA_B200_EXT_NONE = 0,         /* Ebv == 0 / not used                                            */
+    NMMA_B200_EXT_P92_SMC_HOST = 1, /* extinctionFactorP92SMC: Pei (1992) SMC curve in the host frame */
+    NMMA_B200_EXT_LINEAR = 2        /* ext_mag_f = coef_f * Ebv (extinctionFactorG23MW, observer frame) */
+};
+
+#define NMMA_B200_MAX_CONSTRAINTS 8
 #define NMMA_B200_MAX_D 16
 #define NMMA_B200_MAX_K 16
 #define NMMA_B200_MAX_HELPERS 3
@@ -137,6 +148,23 @@ int nmma_b200_set_systematics(nmma_b200_t* h, int G, const int32_t* mode, const 
                               const int32_t* n_nodes, const int32_t* node_offset,
                               const nmma_b200_param_src* node_src, const double* node_times);
 
+/* Constraint priors, NMMALikelihoodMixin.evaluate_constraints (nmma/core/base.py:67-68,77-82;
+ * bilby Constraint.prob = (val > minimum) & (val < maximum)): a point whose value (a column or a
+ * constant, after the transform: KNtheta from inclination_EM, log10 twins) violates any of the n
+ * constraints gets the sentinel.  n == 0 clears them. */
+int nmma_b200_set_constraints(nmma_b200_t* h, int n, const nmma_b200_param_src* src /* n */,
+                              const double* minimum /* n */, const double* maximum /* n */);
+/* Extinction, LightCurveModelContainer.get_extinction_mags / apply_extinction_correction
+ * (nmma/em/model.py:323-350) with extinctionFactorP92SMC / extinctionFactorG23MW
+ * (nmma/em/utils.py:373-466): ext_mag_f is added to the absolute magnitudes of model filter f
+ * before the distance modulus.  `ebv` is the Ebv column or constant.  law P92_SMC_HOST: nu0[F] =
+ * c / wave_eff of each model filter in Hz (0 = filter unknown to get_default_filts_lambdas: left
+ * uncorrected), evaluated per point at nu0 (1+z); coef ignored.  law LINEAR: coef[F] =
+ * A_f / E(B-V) (R_V x the curve at the observer-frame wavelength); nu0 ignored.  law NONE: both
+ * may be NULL.  Call after nmma_b200_set_svd (which resets it). */
+int nmma_b200_set_extinction(nmma_b200_t* h, int law, nmma_b200_param_src ebv, const double* nu0 /* F */,
+                             const double* coef /* F */);
+
 /* ---- compute ----------------------------------------------------------- */
 /* EMTransientLikelihood.log_likelihood for N points (nmma/core/base.py:77-82,178-182
  * -> nmma/em/em_likelihood.py:186-204): out[i] is log L or the reference's sentinel
@@ -146,9 +174,12 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev /* N*P */, int64_t N
 /* Same through HOST buffers: pinned staging, H2D, kernels, D2H, synchronised on return.
  * This is the call an unmodified one-point-at-a-time sampler ends up in.  Large batches
  * are cut into row blocks (option "pipeline_blocks", default 6) whose copies overlap the
- * kernels of their neighbours on separate streams.  out_host may also be a DEVICE
- * pointer: the result then stays on the GPU (the sharded path gathers it with NCCL). */
+ * kernels of their neighbours on separate streams.  Both pointers must be host memory. */
 int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host);
+/* Same input side, but the result stays on the GPU in out_dev[N] (no D2H copy): the sharded
+ * path gathers it with NCCL, the analogue of the reference's MPI result gather
+ * (nmma/core/mpi_setup.py:651-683).  Synchronised on return. */
+int nmma_b200_logl_host_to_device(nmma_b200_t* h, const double* points_host, int64_t N, double* out_dev);
 /* SVDLightCurveModel.generate_lightcurve (apparent == 0, nmma/em/model.py:707-728:
  * absolute mags on the sample grid, +inf outside the training time range) or
  * gen_detector_lc (apparent == 1, nmma/em/model.py:352-404: detector-frame times and
@@ -229,6 +260,11 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value);
  * (SURVEY.md 8d): runs `iters` dependent-chain FMA rounds on every SM and returns
  * the achieved FLOP/s for scalar (variant 0) or packed f32x2 (variant 1) FMAs. */
 int nmma_b200_ffma_peak(nmma_b200_t* h, int variant, int iters, double* flops_per_s);
+/* Dense tcgen05 kind::tf32 rate (the tensor-core kernel's roofline denominator): `iters` x 2
+ * MMAs of 128x128x8 per SM, A from TMEM, B from shared memory; FLOP/s over all SMs. */
+int nmma_b200_tf32_peak(nmma_b200_t* h, int iters, double* flops_per_s);
+/* fp64 FMA rate (the GP front end's roofline denominator), same construction as ffma_peak. */
+int nmma_b200_dfma_peak(nmma_b200_t* h, int iters, double* flops_per_s);
 
 /* Diagnostic: the per-observation term of chisquare_gaussianlog_from_lc_data
  * (nmma/em/em_likelihood.py:224-256: truncnorm.logpdf for finite sigma, norm.logsf for

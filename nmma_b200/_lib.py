@@ -17,7 +17,9 @@ Z_ZERO, Z_PARAM, Z_TABLE = 0, 1, 2
 SYS_BUDGET, SYS_PARAM, SYS_INTERP = 0, 1, 2
 (PR_UNIFORM, PR_DELTA, PR_SINE, PR_COSINE, PR_GAUSSIAN, PR_TRUNC_GAUSS, PR_POWERLAW, PR_TRIANGULAR,
  PR_INTERPED) = range(9)
+EXT_NONE, EXT_P92_SMC_HOST, EXT_LINEAR = 0, 1, 2
 MAX_P = 32
+MAX_CONSTRAINTS = 8
 
 
 class ParamSrc(C.Structure):
@@ -58,8 +60,11 @@ SIGNATURES = {
     "nmma_b200_set_redshift_table": (C.c_int, [_h, C.c_int, _dp, _dp]),
     "nmma_b200_set_observations": (C.c_int, [_h, C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _dp]),
     "nmma_b200_set_systematics": (C.c_int, [_h, C.c_int, _ip, _dp, _ip, _ip, _sp, _dp]),
+    "nmma_b200_set_constraints": (C.c_int, [_h, C.c_int, _sp, _dp, _dp]),
+    "nmma_b200_set_extinction": (C.c_int, [_h, C.c_int, ParamSrc, _dp, _dp]),
     "nmma_b200_logl": (C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nmma_b200_logl_host": (C.c_int, [_h, _dp, C.c_int64, _dp]),
+    "nmma_b200_logl_host_to_device": (C.c_int, [_h, _dp, C.c_int64, C.c_void_p]),
     "nmma_b200_mags": (C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmma_b200_coeffs": (C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nmma_b200_set_priors": (C.c_int, [_h, C.c_int, _ip, _dp, _ip, _dp, _dp]),
@@ -69,6 +74,8 @@ SIGNATURES = {
     "nmma_b200_set_option": (C.c_int, [_h, C.c_char_p, C.c_int64]),
     "nmma_b200_get_info": (C.c_int, [_h, C.c_char_p, C.POINTER(C.c_int64)]),
     "nmma_b200_ffma_peak": (C.c_int, [_h, C.c_int, C.c_int, _dp]),
+    "nmma_b200_tf32_peak": (C.c_int, [_h, C.c_int, _dp]),
+    "nmma_b200_dfma_peak": (C.c_int, [_h, C.c_int, _dp]),
     "nmma_b200_obs_terms": (C.c_int, [_h, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
 }
 

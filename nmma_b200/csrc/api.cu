@@ -128,6 +128,20 @@ int finalize(nmma_b200_t* h, bool need_obs) {
     c.nz = (int)h->zd.size();
     if (int rc = upload(h, h->zd, &c.zd)) return rc;
     if (int rc = upload(h, h->zz, &c.zz)) return rc;
+    c.ncon = (int)h->con_src.size();
+    for (int i = 0; i < c.ncon; ++i) {
+        if (int rc = check_src(h, h->con_src[i], "constraint")) return rc;
+        c.con_src[i] = h->con_src[i]; c.con_lo[i] = h->con_lo[i]; c.con_hi[i] = h->con_hi[i];
+    }
+    c.ext_law = h->ext_law;
+    c.ebv = h->ebv;
+    if (h->ext_law != 0) {
+        if (int rc = check_src(h, h->ebv, "Ebv")) return rc;
+        if ((int)h->ext_nu.size() != F || (int)h->ext_coef.size() != F)
+            return fail(h, NMMA_B200_ERR_ARG, "extinction tables describe %zu filters, surrogate has F=%d", h->ext_nu.size(), F);
+        if (int rc = upload(h, h->ext_nu, &c.ext_nu)) return rc;
+        if (int rc = upload(h, h->ext_coef, &c.ext_coef)) return rc;
+    }
 
     // ---- basis pack + input scaling ----
     std::vector<double> pden((size_t)F * d), bpack((size_t)F * T * (K + 2));
@@ -474,6 +488,7 @@ int nmma_b200_set_svd(nmma_b200_t* h, int F, int d, int K, int T, const double* 
     h->maxs.assign(maxs, maxs + FT);
     h->have_svd = true;
     h->kind = -1;
+    h->ext_law = 0;   // per-filter extinction tables belong to the previous filter set
     h->dirty = true;
     return NMMA_B200_OK;
 }
@@ -609,6 +624,48 @@ int nmma_b200_set_systematics(nmma_b200_t* h, int G, const int32_t* mode, const 
     return NMMA_B200_OK;
 }
 
+int nmma_b200_set_constraints(nmma_b200_t* h, int n, const nmma_b200_param_src* src, const double* minimum,
+                              const double* maximum) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (n < 0 || n > kMaxCon) return fail(h, NMMA_B200_ERR_UNSUPPORTED, "set_constraints: %d constraints (0..%d supported)", n, kMaxCon);
+    if (n > 0 && (!src || !minimum || !maximum)) return fail(h, NMMA_B200_ERR_ARG, "set_constraints: NULL array");
+    h->con_src.clear(); h->con_lo.clear(); h->con_hi.clear();
+    for (int i = 0; i < n; ++i) {
+        if (std::isnan(minimum[i]) || std::isnan(maximum[i])) return fail(h, NMMA_B200_ERR_ARG, "set_constraints: NaN bound");
+        h->con_src.push_back(to_src(src[i]));
+        h->con_lo.push_back(minimum[i]);
+        h->con_hi.push_back(maximum[i]);
+    }
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
+int nmma_b200_set_extinction(nmma_b200_t* h, int law, nmma_b200_param_src ebv, const double* nu0, const double* coef) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (!h->have_svd) return fail(h, NMMA_B200_ERR_STATE, "set_extinction: call nmma_b200_set_svd first");
+    if (law < NMMA_B200_EXT_NONE || law > NMMA_B200_EXT_LINEAR) return fail(h, NMMA_B200_ERR_ARG, "set_extinction: unknown law %d", law);
+    const int F = h->F;
+    h->ext_law = law;
+    h->ebv = to_src(ebv);
+    h->ext_nu.assign(F, 0.0);
+    h->ext_coef.assign(F, 0.0);
+    if (law == NMMA_B200_EXT_P92_SMC_HOST) {
+        if (!nu0) return fail(h, NMMA_B200_ERR_ARG, "set_extinction: P92_SMC_host needs the filter frequencies nu0[F]");
+        for (int f = 0; f < F; ++f) {
+            if (std::isnan(nu0[f]) || nu0[f] < 0.0 || std::isinf(nu0[f])) return fail(h, NMMA_B200_ERR_ARG, "set_extinction: nu0[%d] must be finite and >= 0", f);
+            h->ext_nu[f] = nu0[f];
+        }
+    } else if (law == NMMA_B200_EXT_LINEAR) {
+        if (!coef) return fail(h, NMMA_B200_ERR_ARG, "set_extinction: the linear law needs coef[F] = A_f / E(B-V)");
+        for (int f = 0; f < F; ++f) {
+            if (!std::isfinite(coef[f])) return fail(h, NMMA_B200_ERR_ARG, "set_extinction: coef[%d] is not finite", f);
+            h->ext_coef[f] = coef[f];
+        }
+    }
+    h->dirty = true;
+    return NMMA_B200_OK;
+}
+
 int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* out_dev, void* stream) {
     if (!h) return NMMA_B200_ERR_ARG;
     if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "logl: N < 0");
@@ -659,17 +716,12 @@ static bool is_device_mem(const void* p) {
 
 constexpr int64_t kZeroCopyMax = 256;   // rows up to which nmma_b200_logl_host skips the staging copies
 
-int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host) {
-    if (!h) return NMMA_B200_ERR_ARG;
-    if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "logl_host: N < 0");
-    if (int rc = finalize(h, true)) return rc;
-    if (N == 0) return NMMA_B200_OK;
-    if (!points_host || !out_host) return fail(h, NMMA_B200_ERR_ARG, "logl_host: NULL pointer");
-    CU(cudaSetDevice(h->device));
+// Shared body of nmma_b200_logl_host (out_dev == false: `out_host` is host memory) and nmma_b200_logl_host_to_device
+// (out_dev == true: `out_host` is a device pointer, the result stays on the GPU and no D2H copy is made).
+static int logl_host_impl(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host, bool out_dev) {
     const size_t nin = (size_t)N * h->P, nout = (size_t)N;
     // page-locked caller buffers are copied directly; pageable ones go through pinned staging
-    // a DEVICE out pointer keeps the result on the GPU (no D2H): the sharded path gathers it with NCCL
-    const bool in_pinned = is_pinned_host(points_host), out_dev = is_device_mem(out_host);
+    const bool in_pinned = is_pinned_host(points_host);
     const bool out_pinned = out_dev || is_pinned_host(out_host);
     if (nin > h->stage_cap_in) {
         if (h->stage_in_dev) cudaFree(h->stage_in_dev);
@@ -740,6 +792,30 @@ int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, do
     }
     if (!out_pinned) std::memcpy(out_host, h->stage_out_host, nout * sizeof(double));
     return NMMA_B200_OK;
+}
+
+int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "logl_host: N < 0");
+    if (int rc = finalize(h, true)) return rc;
+    if (N == 0) return NMMA_B200_OK;
+    if (!points_host || !out_host) return fail(h, NMMA_B200_ERR_ARG, "logl_host: NULL pointer");
+    CU(cudaSetDevice(h->device));
+    if (is_device_mem(points_host) || is_device_mem(out_host))
+        return fail(h, NMMA_B200_ERR_ARG, "logl_host: device pointer passed (use nmma_b200_logl, or nmma_b200_logl_host_to_device for a device result)");
+    return logl_host_impl(h, points_host, N, out_host, false);
+}
+
+int nmma_b200_logl_host_to_device(nmma_b200_t* h, const double* points_host, int64_t N, double* out_dev) {
+    if (!h) return NMMA_B200_ERR_ARG;
+    if (N < 0) return fail(h, NMMA_B200_ERR_ARG, "logl_host_to_device: N < 0");
+    if (int rc = finalize(h, true)) return rc;
+    if (N == 0) return NMMA_B200_OK;
+    if (!points_host || !out_dev) return fail(h, NMMA_B200_ERR_ARG, "logl_host_to_device: NULL pointer");
+    CU(cudaSetDevice(h->device));
+    if (is_device_mem(points_host) || !is_device_mem(out_dev))
+        return fail(h, NMMA_B200_ERR_ARG, "logl_host_to_device: points must be host memory and out a device pointer on this handle's GPU");
+    return logl_host_impl(h, points_host, N, out_dev, true);
 }
 
 int nmma_b200_coeffs(nmma_b200_t* h, const double* points_dev, int64_t N, double* coeffs_dev, void* stream) {

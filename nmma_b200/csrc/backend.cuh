@@ -9,6 +9,7 @@ namespace nmma {
 constexpr int kMaxD = 16;
 constexpr int kMaxK = 16;
 constexpr int kMaxSysNodes = 16;
+constexpr int kMaxCon = 8;   // Constraint priors evaluated per point (nmma_b200_set_constraints)
 
 // Passed by value to every kernel (fits the 4 KB parameter space).
 struct DevCfg {
@@ -74,10 +75,19 @@ struct DevCfg {
     // fused-kernel schedule: observed filters that map directly onto model filter f
     const int* f_goff;    // F+1
     const int* f_glist;
+    // Constraint priors (nmma/core/base.py:67-68): the point fails unless lo < value < hi for every entry
+    int ncon;
+    ParamSrc con_src[kMaxCon];
+    double con_lo[kMaxCon], con_hi[kMaxCon];
+    // extinction (nmma/em/model.py:323-350): 0 none, 1 P92 SMC in the host frame, 2 per-filter coefficient x Ebv
+    int ext_law;
+    ParamSrc ebv;
+    const double* ext_nu;    // F  observer-frame frequency nu_0 = c / wave_eff of each model filter [Hz]; 0 = no entry
+    const double* ext_coef;  // F  law 2: A_f / E(B-V) (e.g. the G23 Milky-Way curve at the observer-frame wavelength)
 };
 
 struct PointScal {
-    double z1, ts, dm, zc;
+    double z1, ts, dm, zc, ebv;
     float ga, gb, dmz;  // FAST back end: index guess = fma((float)t, ga, gb) on a uniform grid; dm + zc in fp32
     bool bad;
 };
@@ -103,8 +113,50 @@ __device__ __forceinline__ PointScal point_setup(const DevCfg& cfg, const double
     ps.dm = 5.0 * (5 + log10(dl));
     ps.zc = -2.5 * log10(ps.z1);
     ps.bad = !(isfinite(ps.z1) && isfinite(ps.ts));
+    ps.ebv = 0.0;
+    if (cfg.ext_law != 0) {
+        ps.ebv = eval_src(cfg.ebv, row);
+        ps.bad = ps.bad || !isfinite(ps.ebv);   // NaN magnitudes in every filter -> sanity_check fails
+    }
+    // evaluate_constraints (nmma/core/base.py:67-68): Constraint.prob = (val > minimum) & (val < maximum)
+    for (int i = 0; i < cfg.ncon; ++i) {
+        const double v = eval_src(cfg.con_src[i], row);
+        ps.bad = ps.bad || !(v > cfg.con_lo[i] && v < cfg.con_hi[i]);
+    }
     point_fast_fields(cfg, ps);
     return ps;
+}
+
+// get_extinction_mags for model filter f (nmma/em/model.py:323-342), added to the absolute magnitudes before the
+// distance modulus (apply_extinction_correction, :344-350).
+//   law 1, extinctionFactorP92SMC (nmma/em/utils.py:373-433): Pei (1992) SMC curve xi(lambda) = sum_i a_i /
+//   ((lambda/lambda_i)^n_i + (lambda_i/lambda)^n_i + b_i) with the six terms of his Table 4 (inline at :398-423),
+//   amplitudes referred to A_V through A_B/A_V = 1/3.08 + 1 (dust_extinction P92.AbAv), evaluated at the HOST-frame
+//   wavelength c / (nu_0 (1+z)) where nu_host lies in [c * 10 cm^-1, 2e16 Hz]; A_V = 2.93 Ebv;
+//   ext_mag = -2.5 log10(10^(-0.4 xi A_V)).
+//   law 2, extinctionFactorG23MW (:436-466): observer-frame, redshift-independent: ext_mag = coef_f * Ebv with
+//   coef_f = R_V A(lambda_f)/A(V) staged by the host.
+__device__ __forceinline__ double p92_term(double lam, double amp, double cen, double b, bool quartic) {
+    const double l = lam / cen;
+    double p = l * l, q = 1.0 / p;   // np.power(l, n), np.power(l, -n) for n = 2.0
+    if (quartic) { p = p * p; q = 1.0 / p; }
+    return amp / (p + q + b);
+}
+__device__ __forceinline__ double ext_mag(const DevCfg& cfg, int f, const PointScal& ps) {
+    if (cfg.ext_law == 0 || ps.ebv == 0.0) return 0.0;
+    if (cfg.ext_law == 2) return -2.5 * log10(pow(10.0, -0.4 * cfg.ext_coef[f] * ps.ebv));
+    const double nu = cfg.ext_nu[f];
+    if (!(nu > 0.0)) return 0.0;                         // filter without a wavelength entry: left uncorrected
+    const double c_cgs = 29979245800.0;
+    const double nu_host = nu * ps.z1;
+    if (!(nu_host >= 1e-3 * 1e4 * c_cgs && nu_host <= 2e16)) return -2.5 * log10(1.0);
+    const double lam = 1.0 / (1.0 / ((c_cgs / nu_host) * 1e4));   // cm -> micron -> 1/micron -> micron, as dust_extinction does
+    const double abav = 1.0 / 3.08 + 1.0;
+    const double ax = p92_term(lam, 185.0 * abav, 0.042, 90.0, false) + p92_term(lam, 27 * abav, 0.08, 5.5, true) +
+                      p92_term(lam, 0.005 * abav, 0.22, -1.95, false) + p92_term(lam, 0.010 * abav, 9.7, -1.95, false) +
+                      p92_term(lam, 0.012 * abav, 18.0, -1.80, false) + p92_term(lam, 0.030 * abav, 25.0, 0.0, false);
+    const double av = 2.93 * ps.ebv;
+    return -2.5 * log10(pow(10.0, -0.4 * ax * av));
 }
 
 // x' = (x - param_mins) / (param_maxs - param_mins), lightcurve_generation.py:193-194.
@@ -173,17 +225,17 @@ __device__ __forceinline__ int locate(const DevCfg& cfg, int lo, int hi, double 
 // Stage 2, update_lightcurve_reference (em_likelihood.py:313-335): apparent magnitude of
 // model filter f at observation time t.  `abs_at(s)` returns the stage-1 absolute mag.
 template <typename AbsFn>
-__device__ __forceinline__ double interp_obs(const DevCfg& cfg, int f, double t, const PointScal& ps, AbsFn abs_at) {
+__device__ __forceinline__ double interp_obs(const DevCfg& cfg, int f, double t, const PointScal& ps, double ext, AbsFn abs_at) {
     const int lo = cfg.s_lo[f], hi = cfg.s_hi[f];
     const double tlo = tobs_at(cfg, lo, ps.z1, ps.ts), thi = tobs_at(cfg, hi, ps.z1, ps.ts);
     if (t < tlo || t > thi) return CUDART_INF;  // left = right = +inf
     const int j = locate(cfg, lo, hi, t, ps.z1, ps.ts);
     const double tj = tobs_at(cfg, j, ps.z1, ps.ts);
-    // mags + distmod + redshift_correction, em/model.py:396
-    const double aj = __dadd_rn(__dadd_rn(abs_at(j), ps.dm), ps.zc);
+    // (mags + ext_mag) + distmod + redshift_correction, em/model.py:347,396
+    const double aj = __dadd_rn(__dadd_rn(__dadd_rn(abs_at(j), ext), ps.dm), ps.zc);
     if (j == hi || tj == t) return aj;
     const double tj1 = tobs_at(cfg, j + 1, ps.z1, ps.ts);
-    const double aj1 = __dadd_rn(__dadd_rn(abs_at(j + 1), ps.dm), ps.zc);
+    const double aj1 = __dadd_rn(__dadd_rn(__dadd_rn(abs_at(j + 1), ext), ps.dm), ps.zc);
     const double slope = __ddiv_rn(__dsub_rn(aj1, aj), __dsub_rn(tj1, tj));
     double r = __dadd_rn(__dmul_rn(slope, __dsub_rn(t, tj)), aj);
     if (isnan(r)) {

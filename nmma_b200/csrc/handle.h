@@ -42,6 +42,12 @@ struct nmma_b200_handle {
     std::vector<int> sy_mode, sy_nn, sy_off;
     std::vector<double> sy_budget, sy_t;
     std::vector<nmma::ParamSrc> sy_src;
+    // Constraint priors and extinction (api.cu: nmma_b200_set_constraints / nmma_b200_set_extinction)
+    std::vector<nmma::ParamSrc> con_src;
+    std::vector<double> con_lo, con_hi;
+    int ext_law = 0;
+    nmma::ParamSrc ebv{-1, 0, 0.0};
+    std::vector<double> ext_nu, ext_coef;
     // ---- priors on the device (prior.cu) ----
     int prP = 0;
     int pr_tab_total = 0;                   // entries in each half (cdf | grid) of pr_tab_dev

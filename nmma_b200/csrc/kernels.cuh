@@ -213,7 +213,9 @@ __device__ __forceinline__ double expected_mag(const DevCfg& cfg, int g, double 
         const int K = cfg.K;
         auto node = [&](int j) { return node_mag(bp, K, j, c); };
         auto abs_at = [&](int s) { return sample_mag(cfg, f, s, node); };
-        const double v = interp_obs(cfg, f, t, ps, abs_at);
+        const double ext = ext_mag(cfg, f, ps);
+        if (!isfinite(ext)) return CUDART_NAN;       // the whole filter is non-finite: sanity_check fails
+        const double v = interp_obs(cfg, f, t, ps, ext, abs_at);
         mu = (hh == 0) ? v : __dadd_rn(mu, v);  // (mag[a] + mag[b] [+ mag[c]]) / n, em/utils.py:566-584
     }
     if (nh == 2) mu = __ddiv_rn(mu, 2.0);
@@ -276,7 +278,10 @@ backend_mags_kernel(const DevCfg cfg, const double* __restrict__ pts, const doub
                 auto node = [&](int j) { return node_mag(bp, K, j, c); };
                 v = sample_mag(cfg, f, s, node);
             }
-            if (apparent) v = __dadd_rn(__dadd_rn(v, ps.dm), ps.zc);
+            if (apparent) {
+                const double ext = ext_mag(cfg, f, ps);
+                v = isfinite(ext) ? __dadd_rn(__dadd_rn(__dadd_rn(v, ext), ps.dm), ps.zc) : CUDART_INF;
+            }
         }
         mags[idx] = v;
         if (tobs != nullptr && f == 0) tobs[n * cfg.S + s] = tobs_at(cfg, s, ps.z1, ps.ts);
@@ -310,13 +315,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Bounded wait: a phase bug must not hang the sampler process (the C ABI promises a status, not a hang).  Every
+// 2^14 failed polls the global timer is read; a single wait that lasts longer than kMbarTimeoutNs traps, the launch
+// ends with cudaErrorLaunchFailure and the API call returns NMMA_B200_ERR_CUDA.  Normal waits last microseconds.
+constexpr unsigned long long kMbarTimeoutNs = 8000000000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    uint32_t polls = 0;
+    unsigned long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++polls & 0x3fffu) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kMbarTimeoutNs) __trap();
+        }
+    }
 }
 // Wait of a warp that is not on the critical path (producer, back end): the hardware may keep the thread suspended for
 // up to `hint_ns` before try_wait returns, so an idle warp does not burn issue slots re-polling the barrier.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 100000u) {
-    uint32_t ok = 0;
+    uint32_t ok = 0, polls = 0;
+    unsigned long long t0 = 0;
     while (!ok) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -325,6 +348,11 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
             : "memory");
+        if (!ok && (++polls & 0xffu) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kMbarTimeoutNs) __trap();
+        }
     }
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0).
@@ -400,7 +428,13 @@ __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, co
     if constexpr (FAST) {
         const float2* __restrict__ bq = reinterpret_cast<const float2*>(bp);
         const int T = cfg.T;
-        const float ga = ps.ga, gb = ps.gb, dmz = ps.dmz;
+        const float ga = ps.ga, gb = ps.gb;
+        float dmz = ps.dmz;
+        if (cfg.ext_law) {
+            const double ext = ext_mag(cfg, f, ps);
+            if (!isfinite(ext)) return CUDART_NAN;   // the whole filter is non-finite: sanity_check fails (em_likelihood.py:305-311)
+            dmz = (float)(ext + ps.dm + ps.zc);
+        }
         const float dlt = cfg.fast_delta, dhi = 1.0f - cfg.fast_delta;
         float c[K];
 #pragma unroll
@@ -500,6 +534,8 @@ __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, co
             }
         }
     } else {
+        const double ext = ext_mag(cfg, f, ps);
+        if (!isfinite(ext)) return CUDART_NAN;
         for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
             const int g = cfg.f_glist[gi];
             const double lim = cfg.g_lim[g];
@@ -510,7 +546,7 @@ __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, co
                 const double t = rec[0], m = rec[1], so = rec[2];
                 auto node = [&](int j) { return node_mag_k<K>(bp, j, cp); };
                 auto abs_at = [&](int s) { return sample_mag(cfg, f, s, node); };
-                const double mu = interp_obs(cfg, f, t, ps, abs_at);
+                const double mu = interp_obs(cfg, f, t, ps, ext, abs_at);
                 if (mode == 0 && isfinite(so)) lsum += obs_term_static_det(m, mu, rec[3], rec[5], lim);
                 else lsum += obs_term(m, mu, so, sys_sigma(cfg, g, t, row), lim);
             }

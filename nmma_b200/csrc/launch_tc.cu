@@ -20,8 +20,12 @@ template <bool FAST>
 int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
     constexpr int K = 10;
     const size_t smem = tc_smem_bytes(K, h->T, h->cfg.S, h->cfg.nobs);
-    CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, FAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, FAST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t attr_smem[2] = {0, 0};   // per instantiation (FAST): the attribute is per function, not per handle
+    if (attr_smem[FAST] < smem) {          // one driver call per configuration instead of two per launch (one-point latency)
+        CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, FAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, FAST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem[FAST] = smem;
+    }
     const long long super = (long long)kTcTile * kTcTiles;
     const long long nsuper = (N + super - 1) / super;
     long long grid = h->sm_count;  // one CTA per SM: each CTA owns all 512 TMEM columns of its SM

@@ -27,6 +27,7 @@ from ..samplers import equal_weight, nested_sample
 from . import io, utils
 from .em_likelihood import EMTransientLikelihood
 from .model import create_light_curve_model_from_args
+from .prior import create_prior_from_args
 from .systematics import FilterSystematicsHandler
 
 __all__ = ["get_parser", "analysis_setup", "analysis", "main"]
@@ -58,6 +59,10 @@ def get_parser() -> argparse.ArgumentParser:
     p.add_argument("--systematics-file", type=str, default=None)
     p.add_argument("--detection-limit", type=float, default=None)
     p.add_argument("--remove-nondetections", action="store_true")
+    p.add_argument("--use-Ebv", dest="use_Ebv", action="store_true", help="sample the extinction E(B-V)")
+    p.add_argument("--Ebv-max", dest="Ebv_max", type=float, default=0.5724)
+    p.add_argument("--em-extinction-law", dest="em_extinction_law", type=str, default=None,
+                   help="P92_SMC_host (default) | G23_MW")
     p.add_argument("--verbose", action="store_true")
     # sampler (replaces bilby's --sampler / --nlive / --seed block)
     p.add_argument("--nlive", type=int, default=1024)
@@ -99,9 +104,7 @@ def analysis_setup(args, svd_mag_model=None):
         light_curve_model = create_light_curve_model_from_args(args.em_model, args, filters=filters_to_analyze)
     light_curve_data = utils.setup_filtered_lc_data(data, trigger_time)
     handler = FilterSystematicsHandler(filters_to_analyze, args.systematics_file, args.em_error_budget, light_curve_data[0])
-    priors = args.prior if isinstance(args.prior, PriorDict) else PriorDict(filename=args.prior)
-    if args.systematics_file is not None:
-        handler.setup_systematics_priors(priors)
+    priors = create_prior_from_args(args, handler)     # prior file + Ebv prior + em_syserr* priors (nmma/em/prior.py:221-244)
     light_curve_data = utils.check_model_time_consistency(light_curve_data, light_curve_model, priors, None)
     handler = FilterSystematicsHandler(filters_to_analyze, args.systematics_file, args.em_error_budget, light_curve_data[0])
     likelihood = EMTransientLikelihood(light_curve_model, light_curve_data, handler, priors, filters=filters_to_analyze,

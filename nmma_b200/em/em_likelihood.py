@@ -22,7 +22,7 @@ from ..core.base import NMMALikelihood
 from ..core.constants import SENTINEL
 from ..core.priors import fixed_value, is_constraint, is_fixed_prior
 from . import utils
-from .model import resolve_param_sources
+from .model import resolve_constraint_sources, resolve_param_sources
 
 
 class MultiFilterTransient:
@@ -49,7 +49,9 @@ class MultiFilterTransient:
         self.verbose = verbose
         self.set_detection_limit(detection_limit)
         self._engine = None
+        self._engines: Dict[tuple, tuple] = {}       # column tuple -> (engine, always_fail); _engine is the last one used
         self._columns: Optional[List[str]] = None
+        self._dict_base: Optional[List[str]] = None  # sampled columns of log_likelihood(dict) calls
         self._always_fail = False
 
     def set_detection_limit(self, detection_limit):
@@ -62,6 +64,7 @@ class MultiFilterTransient:
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_engine"] = None
+        state["_engines"] = {}
         return state
 
     # ---- layout ---------------------------------------------------------------------------
@@ -90,8 +93,16 @@ class MultiFilterTransient:
         plan["xsrc"] = resolve_param_sources(model.model_parameters, avail)
         plan["dl"] = avail.get("luminosity_distance", ParamSrc.const(1e-5))
         plan["ts"] = avail.get("timeshift", ParamSrc.const(0.0))
+        plan["ext"] = None
         if "Ebv" in avail and not (avail["Ebv"].col < 0 and avail["Ebv"].value == 0.0):
-            raise NotImplementedError("extinction (Ebv != 0) is not part of this build (DESIGN.md, 'next' rows)")
+            law, nu0, coef = model.extinction_plan(model._eval_filters)
+            plan["ext"] = (law, avail["Ebv"], nu0, coef)
+        # Constraint priors (nmma/core/base.py:67-68) on a column, a fixed value or a derived key of the conversion chain
+        cons = [(k, p) for k, p in self.priors.items() if is_constraint(p)]
+        plan["constraints"] = None
+        if cons:
+            srcs = resolve_constraint_sources([k for k, _ in cons], model.model_parameters, avail)
+            plan["constraints"] = (srcs, [float(p.minimum) for _, p in cons], [float(p.maximum) for _, p in cons])
         plan["z_table"] = None
         if "redshift" in avail:
             plan["zsrc"], plan["zmode"] = avail["redshift"], L.Z_PARAM
@@ -144,21 +155,69 @@ class MultiFilterTransient:
         eng.set_param_layout(plan["P"], plan["xsrc"], plan["dl"], plan["ts"], plan["zsrc"], plan["zmode"])
         eng.set_observations(*plan["obs"])
         eng.set_systematics(*plan["sys"])
+        if plan["ext"] is not None:
+            eng.set_extinction(*plan["ext"])
+        if plan["constraints"] is not None:
+            eng.set_constraints(*plan["constraints"])
         self._always_fail = plan["always_fail"]
-        if hasattr(self.priors, "device_plan"):
+        if hasattr(self.priors, "device_plan") and all(c in self.priors for c in columns):
             try:
                 eng.set_priors(*self.priors.device_plan(columns))
-            except (NotImplementedError, KeyError):
-                pass        # a column without a device prior: prior_transform / sweep raise ERR_STATE when used
+            except NotImplementedError:
+                pass        # a column whose prior has no device transform: prior_transform / sweep raise ERR_STATE when used
         self._engine = eng
         self._columns = list(columns)
+        self._engines[tuple(columns)] = (eng, self._always_fail)
         return eng
 
     def engine_for(self, columns: Optional[Sequence[str]] = None):
         columns = list(columns) if columns is not None else (self._columns or self.default_columns())
+        if self._engine is None:              # invalidated (new detection limit, unpickled, test hooks): drop every layout
+            self._engines = {}
         if self._engine is None or self._columns != columns:
-            self._build_engine(columns)
+            hit = self._engines.get(tuple(columns))
+            if hit is not None:
+                self._engine, self._always_fail = hit
+                self._columns = list(columns)
+            else:
+                self._build_engine(columns)
         return self._engine
+
+    _ANGLE_KEYS = ("KNtheta", "inclination_EM", "theta_jn", "cos_theta_jn")
+
+    def _dict_columns(self, parameters) -> List[str]:
+        """Columns for ``log_likelihood(dict)``.  The reference evaluates the dict as given
+        (``em_parameter_setup``, nmma/em/model.py:288-303), so besides the sampled keys a key becomes a column when
+        its value is not the constant staged from the priors: a fixed prior given a different value, or a key
+        without a prior that the path reads (``luminosity_distance``, ``timeshift``, ``Ebv``, ``redshift`` when no
+        distance prior exists, a model parameter, the first angle key when none is sampled)."""
+        cols = list(self._dict_base)
+        pri = self.priors
+        have_angle = any(a in cols or a in pri for a in self._ANGLE_KEYS)
+        extra = []
+        for k, v in parameters.items():
+            if k in cols or isinstance(v, (str, bool)) or not np.isscalar(v):
+                continue
+            p = pri.get(k) if k in pri else None
+            if p is not None:
+                if is_constraint(p) or not is_fixed_prior(p) or fixed_value(p) == float(v):
+                    continue
+            elif k in self._ANGLE_KEYS:
+                if have_angle:
+                    continue          # a twin the conversion chain derived from the sampled angle
+                have_angle = True
+            elif k in ("luminosity_distance", "timeshift") or k in self.light_curve_model.model_parameters:
+                pass
+            elif k == "Ebv":
+                if float(v) == 0.0:
+                    continue
+            elif k == "redshift":
+                if "luminosity_distance" in pri or "luminosity_distance" in cols:
+                    continue          # check_vs_priors installed the dL -> z table: the dict's redshift is not read
+            else:
+                continue
+            extra.append(k)
+        return cols + extra
 
     # ---- evaluation -------------------------------------------------------------------------
     def log_likelihood_batch(self, points, columns: Optional[Sequence[str]] = None, out=None):
@@ -196,8 +255,11 @@ class MultiFilterTransient:
 
     def log_likelihood(self, parameters):
         """One point, dict in / float out (``nmma/em/em_likelihood.py:186-204``)."""
-        eng = self.engine_for(None)
-        row = np.array([[parameters[k] for k in self._columns]], float)
+        if self._dict_base is None:
+            self._dict_base = list(self._columns or self.default_columns())
+        cols = self._dict_columns(parameters)
+        eng = self.engine_for(cols)
+        row = np.array([[parameters[k] for k in cols]], float)
         logl = float(eng.logl_host(row)[0])
         if self._always_fail:
             logl = SENTINEL
@@ -233,8 +295,6 @@ class EMTransientLikelihood(NMMALikelihood):
         the dict is evaluated as given."""
         if parameters is None:
             parameters = self.parameters
-        if self.constraints and not self.evaluate_constraints(self.parameter_conversion(dict(parameters))):
-            return SENTINEL
         if not self.sanity_checks():
             return SENTINEL
         return self.sub_log_likelihood(parameters)
@@ -243,10 +303,7 @@ class EMTransientLikelihood(NMMALikelihood):
     def log_likelihood_batch(self, points, columns: Optional[Sequence[str]] = None, out=None):
         """``float64[N]`` log L (or sentinel) for ``points[N, P]``; ``columns`` names the P columns
         (default: sampled prior keys in prior order)."""
-        if self.constraints:
-            raise NotImplementedError("Constraint priors are evaluated per point on the host; "
-                                      "use log_likelihood(dict) or drop the constraint for batched sweeps")
-        return self.sub_model.log_likelihood_batch(points, columns, out=out)
+        return self.sub_model.log_likelihood_batch(points, columns, out=out)   # Constraint priors: on the device
 
     def prior_transform_batch(self, unit, columns: Optional[Sequence[str]] = None):
         """Vectorised ``priors.rescale`` on the device (ultranest ``transform`` with ``vectorized=True``)."""
@@ -258,8 +315,6 @@ class EMTransientLikelihood(NMMALikelihood):
     def log_likelihood_sweep(self, n, seed=0, first_index=0, return_points=False,
                              columns: Optional[Sequence[str]] = None):
         """Prior sweep (BASELINE.json configs[1] and [4]) with the draws made on the device."""
-        if self.constraints:
-            raise NotImplementedError("Constraint priors are evaluated per point on the host")
         return self.sub_model.log_likelihood_sweep(n, seed, first_index, return_points, columns)
 
     def vectorized(self, columns: Optional[Sequence[str]] = None):
@@ -282,34 +337,87 @@ class EMTransientLikelihood(NMMALikelihood):
 
     @property
     def pool(self):
-        return BatchPool(self)
+        if getattr(self, "_pool", None) is None:
+            self._pool = BatchPool(self)
+        return self._pool
 
 
 OpticalLightCurve = None  # set in nmma_b200.em.likelihood (legacy positional signature)
 
 
 class BatchPool:
-    """``pool.map(fn, list_of_theta)`` adapter (dynesty / schwimmbad seam, ``nmma/core/mpi_setup.py:298-303,679``):
-    stacks the points of one sampler iteration and makes a single GPU call; ``fn`` is ignored for
-    likelihood calls issued by the sampler (it *is* this likelihood)."""
+    """``pool.map(fn, iterable)`` adapter for the dynesty / schwimmbad seam
+    (``nmma/core/mpi_setup.py:298-303,679``; dynesty calls ``pool.map(loglikelihood, points)`` and
+    ``pool.map(prior_transform, unit_points)`` with ``queue_size`` points per call).
 
-    def __init__(self, likelihood: EMTransientLikelihood, columns: Optional[Sequence[str]] = None):
+    Hand ``pool.loglike`` (and optionally ``pool.prior_transform``) to the sampler and pass the pool as
+    ``pool=``: a ``map`` whose ``fn`` is one of these (directly, as a bound method of the likelihood, or inside the
+    sampler's wrapper object) stacks the points of the call and makes a single GPU call.  Any other ``fn``
+    (``evolve_point`` with argument objects, user callbacks) is mapped serially, untouched.
+    """
+
+    _UNWRAP = ("func", "loglikelihood", "prior_transform", "__wrapped__", "__func__")
+
+    def __init__(self, likelihood: "EMTransientLikelihood", columns: Optional[Sequence[str]] = None):
         self.likelihood = likelihood
         self.columns = list(columns) if columns is not None else likelihood.columns
         self.size = 1 << 14
 
+    # ---- the callables to give to the sampler -------------------------------------------------------------
+    def loglike(self, theta):
+        """One point (array in ``columns`` order, or dict) -> float log L."""
+        if isinstance(theta, dict):
+            return float(self.likelihood.log_likelihood(theta))
+        row = np.asarray(theta, float).reshape(1, -1)
+        return float(self.likelihood.log_likelihood_batch(row, self.columns)[0])
+
+    def prior_transform(self, unit):
+        """One unit-cube point -> physical point (``priors.rescale``), evaluated on the device."""
+        row = np.asarray(unit, float).reshape(1, -1)
+        return self.likelihood.prior_transform_batch(row, self.columns).cpu().numpy()[0]
+
+    # ---- dispatch -----------------------------------------------------------------------------------------
+    def _role(self, fn):
+        """'loglike' / 'prior' when ``fn`` is (a wrapper around) one of this pool's or likelihood's callables."""
+        lik = self.likelihood
+        seen = 0
+        while fn is not None and seen < 6:
+            owner = getattr(fn, "__self__", None)
+            name = getattr(fn, "__name__", "")
+            if (owner is self or owner is lik or owner is getattr(lik, "sub_model", None)
+                    or (isinstance(owner, BatchPool) and owner.likelihood is lik)):
+                if name in ("loglike", "log_likelihood", "log_likelihood_ratio"):
+                    return "loglike"
+                if name == "prior_transform":
+                    return "prior"
+            nxt = None
+            for attr in self._UNWRAP:
+                cand = getattr(fn, attr, None)
+                if callable(cand) and cand is not fn:
+                    nxt = cand
+                    break
+            fn, seen = nxt, seen + 1
+        return None
+
     def map(self, fn, iterable):
-        thetas = list(iterable)
-        if len(thetas) == 0:
+        items = list(iterable)
+        if not items:
             return []
-        first = thetas[0]
-        if isinstance(first, dict):
-            pts = np.array([[t[k] for k in self.columns] for t in thetas], float)
-        else:
-            pts = np.asarray(thetas, float)
+        role = self._role(fn)
+        if role is None:
+            return [fn(t) for t in items]
+        try:
+            if role == "loglike" and isinstance(items[0], dict):
+                pts = np.array([[t[k] for k in self.columns] for t in items], float)
+            else:
+                pts = np.asarray(items, float)
+        except (TypeError, ValueError, KeyError):
+            return [fn(t) for t in items]
         if pts.ndim != 2 or pts.shape[1] != len(self.columns):
-            return [fn(t) for t in thetas]          # not a likelihood call (e.g. prior transform)
-        return list(self.likelihood.log_likelihood_batch(pts, self.columns))
+            return [fn(t) for t in items]
+        if role == "prior":
+            return list(self.likelihood.prior_transform_batch(pts, self.columns).cpu().numpy())
+        return [float(v) for v in self.likelihood.log_likelihood_batch(pts, self.columns)]
 
     def close(self):
         pass

@@ -92,6 +92,22 @@ def resolve_param_sources(model_parameters: Sequence[str], available: Dict[str, 
     return out
 
 
+def resolve_constraint_sources(keys: Sequence[str], model_parameters: Sequence[str], available: Dict[str, ParamSrc]):
+    """Where the value of each Constraint prior comes from after the reference's conversion chain
+    (``nmma/core/base.py:67-68,77-82``): a sampled column / fixed value as is, or a key the chain derives
+    (``KNtheta`` from the inclination, ``log10_x`` <-> ``x`` twins of model parameters)."""
+    out = []
+    for key in keys:
+        if key in available:
+            out.append(available[key])
+        elif key == "KNtheta" or key in model_parameters:
+            out.append(resolve_param_sources([key], available)[0])
+        else:
+            raise NotImplementedError(f"Constraint on '{key}': the EM conversion chain does not produce this key "
+                                      "(joint GW-EM constraints are outside the nmma_b200 hot path)")
+    return out
+
+
 class LightCurveModelContainer:
     """Parent class (``nmma/em/model.py:175-408``): detector-frame conversion around ``generate_lightcurve``."""
 
@@ -110,8 +126,38 @@ class LightCurveModelContainer:
         if isinstance(filters, str):
             filters = filters.split(",")
         self.filters = filters
+        from . import utils
+        from ..core.constants import c_SI
+        self.default_filts, self.lambdas = utils.get_default_filts_lambdas(self.filters) if self.filters else ([], np.zeros(0))
+        self.nu_0s = c_SI / self.lambdas                  # nmma/em/model.py:223-224
         self.good_parameters = True
         self.model_times = sample_times if sample_times is not None else self.setup_model_times()
+
+    def extinction_plan(self, filters):
+        """Device staging of ``get_extinction_mags`` (``nmma/em/model.py:323-342``) for ``filters`` (the model filters the
+        engine evaluates): ``(law, nu0[F], coef[F])``.  ``nu0 = 0`` marks a filter without a wavelength entry
+        (``apply_extinction_correction`` skips it, :344-350)."""
+        nu0 = np.array([self.nu_0s[self.default_filts.index(f)] if f in self.default_filts else 0.0 for f in filters], float)
+        if self.extinction_law == "P92_SMC_host":
+            return L.EXT_P92_SMC_HOST, nu0, None
+        if self.extinction_law == "G23_MW":
+            # observer-frame, redshift-independent: ext_mag_f = R_V A(lambda_f)/A(V) * Ebv.  The G23 curve itself lives in
+            # the third-party dust_extinction package (absent offline); it is evaluated once per filter at staging time
+            coef = getattr(self, "extinction_coefficients", None)
+            if coef is None:
+                try:
+                    from dust_extinction.parameter_averages import G23
+                    import astropy.units as u
+                except ImportError as exc:
+                    raise NotImplementedError(
+                        "extinction_law 'G23_MW' needs dust_extinction (or model.extinction_coefficients = "
+                        "{filter: A_filter / E(B-V)}) to stage the per-filter coefficients") from exc
+                law = G23(Rv=3.1)
+                x = 1.0 / (self.lambdas * 1e6)
+                coef = {f: (3.1 * float(law(xx / u.micron)) if law.x_range[0] <= xx <= law.x_range[1] else 0.0)
+                        for f, xx in zip(self.default_filts, x)}
+            return L.EXT_LINEAR, None, np.array([float(coef.get(f, 0.0)) for f in filters], float)
+        raise ValueError(f"Unknown extinction_law {self.extinction_law!r}use 'P92_SMC_host' or 'G23_MW'.")
 
     def __repr__(self):
         return self.__class__.__name__ + f"(model={self.model})"
@@ -185,7 +231,7 @@ class SVDLightCurveModel(LightCurveModelContainer):
 
     def __init__(self, model, svd_path=None, svd_mag_ncoeff=None, svd_lbol_ncoeff=None,
                  interpolation_type="keras", model_parameters=None, filters=None, sample_times=None,
-                 local_only=False, svd_mag_model=None, device=0, **em_model_kwargs):
+                 local_only=False, svd_mag_model=None, device=0, extinction_law=None, **em_model_kwargs):
         comps = model.split("_")
         if "tf" in comps:
             comps.remove("tf")
@@ -222,6 +268,8 @@ class SVDLightCurveModel(LightCurveModelContainer):
             raise ValueError(f"No model files found for {model}")
         self.weights: SurrogateWeights = pack_surrogate(core, self._eval_filters, kind, svd_mag_ncoeff)
         self._engine = None
+        if extinction_law is not None:        # create_light_curve_model_from_args, nmma/em/model.py:1611-1613
+            self.extinction_law = extinction_law
 
     # ---- engine plumbing ----------------------------------------------------------------
     def __getstate__(self):
@@ -246,13 +294,16 @@ class SVDLightCurveModel(LightCurveModelContainer):
         return eng
 
     def _canonical_engine(self, sample_times):
-        """Engine whose points are [x_0..x_{d-1}, luminosity_distance, timeshift, redshift]."""
-        if self._engine is None:
+        """Engine whose points are [x_0..x_{d-1}, luminosity_distance, timeshift, redshift, Ebv]."""
+        if self._engine is None or getattr(self, "_engine_law", None) != self.extinction_law:
             eng = self.new_engine()
             d = self.weights.d
-            eng.set_param_layout(d + 3, [ParamSrc.column(i) for i in range(d)],
+            eng.set_param_layout(d + 4, [ParamSrc.column(i) for i in range(d)],
                                  ParamSrc.column(d), ParamSrc.column(d + 1), ParamSrc.column(d + 2), L.Z_PARAM)
+            law, nu0, coef = self.extinction_plan(self._eval_filters)
+            eng.set_extinction(law, ParamSrc.column(d + 3), nu0, coef)
             self._engine = eng
+            self._engine_law = self.extinction_law
             self._engine_grid = None
         st = np.ascontiguousarray(sample_times, float)
         if self._engine_grid is None or self._engine_grid.shape != st.shape or not np.array_equal(self._engine_grid, st):
@@ -275,9 +326,7 @@ class SVDLightCurveModel(LightCurveModelContainer):
 
     def _row(self, parameters):
         plist = self.em_parameter_setup(parameters)
-        if self.Ebv != 0.0:
-            raise NotImplementedError("extinction (Ebv != 0) is not part of this build (DESIGN.md, 'next' rows)")
-        return np.array([list(plist) + [self.luminosity_distance, self.timeshift, self.redshift]], float)
+        return np.array([list(plist) + [self.luminosity_distance, self.timeshift, self.redshift, self.Ebv]], float)
 
     def generate_lightcurve(self, sample_times, parameters, filters="all"):
         """Absolute AB magnitudes on ``sample_times`` per filter (``:707-728``), evaluated on the GPU."""
@@ -331,6 +380,7 @@ def create_light_curve_model_from_args(model_name_arg, args, filters=None, sampl
         raise NotImplementedError("combined light-curve models are outside the nmma_b200 hot path")
     return SVDLightCurveModel(
         names[0], svd_path=getattr(args, "svd_path", None),
+        extinction_law=getattr(args, "em_extinction_law", None),
         svd_mag_ncoeff=getattr(args, "svd_mag_ncoeff", None),
         svd_lbol_ncoeff=getattr(args, "svd_lbol_ncoeff", None),
         interpolation_type=getattr(args, "interpolation_type", "keras"),

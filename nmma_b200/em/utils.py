@@ -44,6 +44,57 @@ _UNPROCESSED = ["u", "g", "r", "i", "z", "y", "J", "H", "K", "X-ray-1keV", "X-ra
 _HARDCODED = {"B": "g", "R": "z", "F160W": "H", "U": "u", "UVW2": "u", "UVW1": "u", "UVM2": "u"}
 
 
+_WAVE_EFF = None
+
+
+def _wave_eff_table():
+    """{sncosmo bandpass name: wave_eff [Angstrom]} from ``nmma_b200/data/wave_eff.json`` (tools/make_wave_eff.py:
+    sncosmo's definition evaluated on the transmission tables vendored in nmma-data; reproduces the six PS1 values the
+    reference hard-codes in ``lambdas_sloan``, nmma/em/utils.py:712-714, to the printed digit)."""
+    global _WAVE_EFF
+    if _WAVE_EFF is None:
+        import json
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "wave_eff.json")
+        with open(path) as fh:
+            _WAVE_EFF = json.load(fh)["wave_eff"]
+    return _WAVE_EFF
+
+
+def get_default_filts_lambdas(filters=None):
+    """``nmma/em/utils.py:680-779``: (filter names, effective wavelengths in metres).  Filters that are neither in the
+    hard-coded list nor a known bandpass are dropped with the reference's warning (they stay uncorrected for extinction)."""
+    from ..core.constants import c_SI
+    eV_per_h_SI = 2.417989242e14          # e / h [Hz per eV] (nmma/core/constants.py)
+    filts = ["u", "g", "r", "i", "z", "y", "J", "H", "K", "U", "B", "V", "R", "I",
+             "radio-1.25GHz", "radio-3GHz", "radio-5.5GHz", "radio-6GHz", "X-ray-1keV", "X-ray-5keV"]
+    lambdas = list(1e-10 * np.array([3561.8, 4866.46, 6214.6, 7687.0, 7127.0, 7544.6, 8679.5, 9633.3, 12350.0]))
+    lambdas += list(1e-10 * np.array([3605.07, 4413.08, 5512.12, 6585.91, 8059.88]))
+    lambdas += list(c_SI / np.array([1.25e9, 3e9, 5.5e9, 6e9]))
+    lambdas += list(c_SI / (np.array([1e3, 5e3]) * eV_per_h_SI))
+    # the reference's list also names sdss::*, swope2::*, FUV, NUV without a wavelength entry (its `filts` is longer than
+    # `lambdas` there, which shifts nothing because lookups go through the bandpass entries appended below)
+    for name, w in _wave_eff_table().items():
+        filts.append(name)
+        lambdas.append(1e-10 * w)
+    if filters is None:
+        return filts, np.array(lambdas)
+    out_f, out_l = [], []
+    for filt in filters:
+        if filt.startswith("radio") and filt not in filts:
+            unit = {"GHz": 1e9, "MHz": 1e6, "kHz": 1e3}.get(filt[-3:])
+            out_f.append(filt); out_l.append(c_SI / (float(filt.replace("radio-", "")[:-3]) * unit))
+        elif filt.startswith("X-ray-") and filt not in filts:
+            unit = {"keV": 1e3, "MeV": 1e6}.get(filt[-3:])
+            out_f.append(filt); out_l.append(c_SI / (float(filt.replace("X-ray-", "")[:-3]) * unit * eV_per_h_SI))
+        elif filt in filts:
+            ii = filts.index(filt)
+            out_f.append(filts[ii]); out_l.append(lambdas[ii])
+        else:
+            print(f"Warning: {filt} not found in filter list.")
+    return out_f, np.array(out_l)
+
+
 def setup_sample_times(args):
     """``nmma/em/utils.py:72-93``."""
     tmin, tmax = args.em_tmin, args.em_tmax

@@ -47,6 +47,7 @@ class KilonovaEngine:
             raise L.NmmaB200Error(rc, msg)
         self.device = int(device)
         self.F = self.d = self.K = self.T = self.P = self.S = 0
+        self.prior_P = 0          # set by set_priors; 0 = no device priors staged
 
     # ---- lifetime -------------------------------------------------------------------
     def close(self):
@@ -152,7 +153,32 @@ class KilonovaEngine:
         self._check(self._lib.nmma_b200_set_systematics(self._h, G, _iptr(mode), _dptr(bud), _iptr(nn), _iptr(off),
                                                         src, _dptr(nt)))
 
+    def set_constraints(self, srcs: Sequence[ParamSrc], minimums, maximums):
+        """Constraint priors (``nmma/core/base.py:67-68``): ``minimum < value < maximum`` or the sentinel."""
+        n = len(srcs)
+        arr = (ParamSrc * max(n, 1))(*srcs)
+        lo, hi = _f64(minimums if n else [0.0]), _f64(maximums if n else [0.0])
+        self._check(self._lib.nmma_b200_set_constraints(self._h, n, arr, _dptr(lo), _dptr(hi)))
+
+    def set_extinction(self, law: int, ebv: ParamSrc = None, nu0=None, coef=None):
+        """Extinction law (``nmma/em/model.py:323-350``): ``nu0[F]`` [Hz] for P92_SMC_host, ``coef[F]`` for the linear law."""
+        ebv = ebv if ebv is not None else ParamSrc.const(0.0)
+        nu = _f64(nu0) if nu0 is not None else None
+        cf = _f64(coef) if coef is not None else None
+        for a in (nu, cf):
+            assert a is None or a.shape == (self.F,)
+        self._check(self._lib.nmma_b200_set_extinction(self._h, int(law), ebv, _dptr(nu) if nu is not None else None,
+                                                       _dptr(cf) if cf is not None else None))
+
     # ---- compute ----------------------------------------------------------------------
+    @staticmethod
+    def _check_out(out, n, device):
+        """A caller-supplied result tensor goes straight to the C ABI: it must be exactly what the kernel writes."""
+        import torch
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.float64 and out.is_contiguous()
+                and out.numel() == n and out.device == device):
+            raise ValueError(f"out must be a contiguous float64 CUDA tensor with {n} elements on {device}")
+
     @staticmethod
     def _stream():
         import torch
@@ -177,6 +203,8 @@ class KilonovaEngine:
         N = pts.shape[0]
         if out is None:
             out = torch.empty(N, dtype=torch.float64, device=pts.device)
+        else:
+            self._check_out(out, N, pts.device)
         with torch.cuda.device(pts.device):
             self._check(self._lib.nmma_b200_logl(self._h, C.c_void_p(pts.data_ptr()), N,
                                                  C.c_void_p(out.data_ptr()), self._stream()))
@@ -194,9 +222,9 @@ class KilonovaEngine:
             out = np.empty(pts.shape[0], np.float64)
         if hasattr(out, "is_cuda"):        # CUDA tensor: the result stays on the device (sharded path, NCCL gather next)
             import torch
-            assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() == pts.shape[0]
-            self._check(self._lib.nmma_b200_logl_host(self._h, _dptr(pts), pts.shape[0],
-                                                      C.cast(C.c_void_p(out.data_ptr()), C.POINTER(C.c_double))))
+            self._check_out(out, pts.shape[0], torch.device(f"cuda:{self.device}"))
+            self._check(self._lib.nmma_b200_logl_host_to_device(self._h, _dptr(pts), pts.shape[0],
+                                                                C.c_void_p(out.data_ptr())))
             return out
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == pts.shape[0]
         self._check(self._lib.nmma_b200_logl_host(self._h, _dptr(pts), pts.shape[0], _dptr(out)))
@@ -256,6 +284,11 @@ class KilonovaEngine:
             self._check(self._lib.nmma_b200_set_priors(self._h, P, _iptr(kinds), _dptr(par), _iptr(off), None, None))
         self.prior_P = P
 
+    def _need_priors(self, what):
+        if not self.prior_P:
+            raise L.NmmaB200Error(L.ERR_STATE, f"{what}: no device priors staged (set_priors was not called or a "
+                                               "column's prior has no device transform)")
+
     def prior_transform(self, unit, out=None):
         """``PriorDict.rescale`` of a CUDA (or NumPy -> copied) ``unit[N,P]``; returns a CUDA tensor."""
         import torch
@@ -265,10 +298,14 @@ class KilonovaEngine:
                 raise ValueError("tensor input must live on the GPU; pass a NumPy array for host data")
         else:
             u = torch.from_numpy(_f64(unit)).to(f"cuda:{self.device}")
+        self._need_priors("prior_transform")
         if u.ndim != 2 or u.shape[1] != self.prior_P:
             raise ValueError(f"unit cube must have shape [N, {self.prior_P}], got {tuple(u.shape)}")
         if out is None:
             out = torch.empty_like(u)
+        elif not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.float64 and out.is_contiguous()
+                  and out.shape == u.shape and out.device == u.device):
+            raise ValueError("out must be a contiguous float64 CUDA tensor shaped like the unit cube")
         with torch.cuda.device(u.device):
             self._check(self._lib.nmma_b200_prior_transform(self._h, C.c_void_p(u.data_ptr()), u.shape[0],
                                                             C.c_void_p(out.data_ptr()), self._stream()))
@@ -277,6 +314,7 @@ class KilonovaEngine:
     def prior_sample(self, n: int, seed: int = 0, first_index: int = 0, return_unit: bool = False):
         """``n`` prior draws on the device (Philox4x32-10 keyed by ``seed``, counter = global point index)."""
         import torch
+        self._need_priors("prior_sample")
         dev = torch.device(f"cuda:{self.device}")
         pts = torch.empty((int(n), self.prior_P), dtype=torch.float64, device=dev)
         unit = torch.empty_like(pts) if return_unit else None
@@ -289,9 +327,12 @@ class KilonovaEngine:
     def logl_sweep(self, n: int, seed: int = 0, first_index: int = 0, return_points: bool = False, out=None):
         """log L of ``n`` prior draws without host traffic (``nmma_b200_logl_sweep``)."""
         import torch
+        self._need_priors("logl_sweep")
         dev = torch.device(f"cuda:{self.device}")
         if out is None:
             out = torch.empty(int(n), dtype=torch.float64, device=dev)
+        else:
+            self._check_out(out, int(n), dev)
         pts = torch.empty((int(n), self.prior_P), dtype=torch.float64, device=dev) if return_points else None
         with torch.cuda.device(dev):
             self._check(self._lib.nmma_b200_logl_sweep(
@@ -311,4 +352,16 @@ class KilonovaEngine:
     def ffma_peak(self, variant: int = 0, iters: int = 20000) -> float:
         v = C.c_double()
         self._check(self._lib.nmma_b200_ffma_peak(self._h, int(variant), int(iters), C.byref(v)))
+        return float(v.value)
+
+    def tf32_peak(self, iters: int = 20000) -> float:
+        """Dense tcgen05 kind::tf32 FLOP/s measured on this device (roofline denominator of the tensor-core kernel)."""
+        v = C.c_double()
+        self._check(self._lib.nmma_b200_tf32_peak(self._h, int(iters), C.byref(v)))
+        return float(v.value)
+
+    def dfma_peak(self, iters: int = 20000) -> float:
+        """fp64 FMA FLOP/s measured on this device (roofline denominator of the GP front end)."""
+        v = C.c_double()
+        self._check(self._lib.nmma_b200_dfma_peak(self._h, int(iters), C.byref(v)))
         return float(v.value)

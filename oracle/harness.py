@@ -30,16 +30,23 @@ def is_fixed(prior):
 
 def build_oracle_likelihood(core, model_parameters, model_filters, sample_times, obs_filters,
                             light_curve_data, priors, sys_plan=None, error_budget=1.0,
-                            detection_limit=np.inf, mag_ncoeff=None, z_table=None):
+                            detection_limit=np.inf, mag_ncoeff=None, z_table=None, filts_lambdas=None,
+                            extinction_law=None, extinction_coef=None):
     """Returns (oracle likelihood, fixed-parameter dict).
 
     ``sys_plan``: output of ``FilterSystematicsHandler.device_plan()`` (host-side map construction is
     not part of the per-point path) or None for a constant ``error_budget``.
     """
     ocore = oracle_core(core)
+    dfilts, lambdas = filts_lambdas if filts_lambdas is not None else (None, None)
     model = O.OracleSVDLightCurveModel(model_parameters, ocore, filters=model_filters,
-                                       sample_times=sample_times, mag_ncoeff=mag_ncoeff)
-    fixed = {k: float(getattr(p, "peak", p)) for k, p in priors.items() if is_fixed(p)}
+                                       sample_times=sample_times, mag_ncoeff=mag_ncoeff, default_filts=dfilts,
+                                       lambdas=lambdas, extinction_coef=extinction_coef)
+    if extinction_law is not None:
+        model.extinction_law = extinction_law
+    is_con = lambda p: p.__class__.__name__ == "Constraint"  # noqa: E731
+    constraints = {k: (p.minimum, p.maximum) for k, p in priors.items() if is_con(p)}
+    fixed = {k: float(getattr(p, "peak", p)) for k, p in priors.items() if is_fixed(p) and not is_con(p)}
     if "redshift" not in priors and "luminosity_distance" in priors:
         dl = priors["luminosity_distance"]
         if z_table is not None:
@@ -65,7 +72,7 @@ def build_oracle_likelihood(core, model_parameters, model_filters, sample_times,
     sys_filters = list(sys_plan.keys()) if sys_plan is not None else list(obs_filters)
     sysh = O.OracleFilterSystematics(sys_filters, times, budget=budget, direct=direct, interp=interp)
     lik = O.OracleMultiFilterTransient(obs_filters, model, light_curve_data, sysh,
-                                       detection_limit=detection_limit)
+                                       detection_limit=detection_limit, constraints=constraints)
     return lik, fixed
 
 

@@ -27,6 +27,7 @@ import numpy as np
 from scipy.stats import norm, truncnorm
 
 from . import cosmology as _cosmo
+from . import extinction as _ext
 
 SENTINEL = float(np.nan_to_num(-np.inf))  # -1.7976931348623157e308, nmma/core/base.py:82
 
@@ -144,8 +145,15 @@ def distance_modulus_nmma(d_lum=1e-5):
 class OracleSVDLightCurveModel:
     """``nmma/em/model.py:175-408`` (base container) + ``:535-731`` (SVD model)."""
 
+    extinction_law = "P92_SMC_host"   # nmma/em/model.py:201
+
     def __init__(self, model_parameters, svd_mag_model, filters=None, sample_times=None,
-                 mag_ncoeff=None):
+                 mag_ncoeff=None, default_filts=None, lambdas=None, extinction_coef=None):
+        # em/model.py:223-224: (default_filts, lambdas) = get_default_filts_lambdas(filters); nu_0s = c_SI / lambdas.
+        # The table comes from sncosmo's bandpass registry in the reference; here it is handed in by the caller.
+        self.default_filts = list(default_filts) if default_filts is not None else []
+        self.nu_0s = 299792458.0 / np.asarray(lambdas, float) if lambdas is not None else np.zeros(0)
+        self.extinction_coef = extinction_coef   # {filter: A_f / E(B-V)}: stands in for the G23 curve (dust_extinction absent)
         self.model_parameters = list(model_parameters)
         self.svd_mag_model = svd_mag_model
         self.filters = list(filters) if filters is not None else list(svd_mag_model.keys())
@@ -211,12 +219,17 @@ class OracleSVDLightCurveModel:
             sample_times = self.model_times
         model_lc = self.generate_lightcurve(sample_times, parameters)
         observable_times = sample_times * (1 + self.redshift) + self.timeshift
-        if self.Ebv != 0.0:
-            raise NotImplementedError("extinction is outside the pinned oracle (dust_extinction absent)")
+        # get_extinction_mags + apply_extinction_correction, em/model.py:323-350,381-386
+        coef = None
+        if self.extinction_coef is not None:
+            coef = [self.extinction_coef.get(f, 0.0) for f in self.default_filts]
+        ext_mag = _ext.get_extinction_mags(self.nu_0s, self.Ebv, self.redshift, self.extinction_law, coef)
+        for em, filt in zip(ext_mag, self.default_filts):
+            if filt in model_lc:
+                model_lc[filt] = model_lc[filt] + em
         redshift_correction = -2.5 * np.log10(1 + self.redshift)
         lc_data = {}
         for filt, mags in model_lc.items():
-            mags = mags + 0.0  # apply_extinction_correction with ext_mag = 0
             if np.sum(np.isfinite(mags)) >= 2:
                 lc_data[filt] = mags + self.distmod + redshift_correction
             else:
@@ -301,7 +314,8 @@ class OracleMultiFilterTransient:
     """``nmma/em/em_likelihood.py:136-352`` wrapped by ``nmma/core/base.py:77-82,178-182``."""
 
     def __init__(self, filters, light_curve_model, light_curve_data, systematics,
-                 detection_limit=np.inf, known_filters=None):
+                 detection_limit=np.inf, known_filters=None, constraints=None):
+        self.constraints = dict(constraints or {})   # {key: (minimum, maximum)} of the Constraint priors
         self.observed_filters = list(filters)
         known = set(known_filters) if known_filters is not None else set(light_curve_model.filters)
         self.model_filter_mapping, self.obs_average_mapping = get_filter_name_mapping(filters, known)
@@ -380,11 +394,12 @@ class OracleMultiFilterTransient:
         obs_error = self.systematics_handler(parameters)
         return self.band_log_likelihood(expected, obs_error)
 
-    # core/base.py:77-82, 178-182 (no Constraint priors in the kilonova configs)
+    # core/base.py:67-68,77-82,178-182; bilby Constraint.prob = (val > minimum) & (val < maximum)
     def log_likelihood(self, parameters):
         with np.errstate(all="ignore"):
             parameters = self.light_curve_model.parameter_conversion(dict(parameters))
-            if not self.light_curve_model.good_parameters:
+            ok = np.prod([(parameters[k] > lo) & (parameters[k] < hi) for k, (lo, hi) in self.constraints.items()])
+            if not (ok and self.light_curve_model.good_parameters):
                 return SENTINEL
             logl = self.sub_log_likelihood(parameters)
         if not np.isfinite(logl):

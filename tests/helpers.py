@@ -80,7 +80,7 @@ def synthetic_observations(filters, rng, n_per_filter=8, tmin=0.3, tmax=12.0, n_
 
 def build_pair(core, model_name, model_filters, obs_filters, lc_data, priors, kind="mlp",
                sample_times=None, error_budget=1.0, systematics=None, detection_limit=np.inf,
-               model_parameters=None):
+               model_parameters=None, extinction_law=None, extinction_coef=None):
     """(GPU likelihood, oracle likelihood, fixed dict, columns)."""
     from nmma_b200.em import EMTransientLikelihood, FilterSystematicsHandler, SVDLightCurveModel
     from oracle import harness
@@ -88,7 +88,9 @@ def build_pair(core, model_name, model_filters, obs_filters, lc_data, priors, ki
     itype = "sklearn_gp" if kind == "gp" else "tensorflow"
     model = SVDLightCurveModel(model_name, svd_mag_model=core, interpolation_type=itype,
                                filters=list(model_filters), sample_times=sample_times,
-                               model_parameters=model_parameters)
+                               model_parameters=model_parameters, extinction_law=extinction_law)
+    if extinction_coef is not None:
+        model.extinction_coefficients = dict(extinction_coef)
     handler = FilterSystematicsHandler(list(obs_filters), systematics, error_budget, lc_data[0])
     if systematics is not None:
         handler.setup_systematics_priors(priors)
@@ -98,7 +100,8 @@ def build_pair(core, model_name, model_filters, obs_filters, lc_data, priors, ki
     olik, fixed = harness.build_oracle_likelihood(
         oracle_ready_core(core), model.model_parameters, list(model_filters), np.asarray(model.model_times, float),
         list(obs_filters), lc_data, priors, sys_plan=plan, detection_limit=detection_limit,
-        z_table=model._z_table)
+        z_table=model._z_table, filts_lambdas=(model.default_filts, model.lambdas), extinction_law=extinction_law,
+        extinction_coef=extinction_coef)
     return lik, olik, fixed, lik.columns
 
 

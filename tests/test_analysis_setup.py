@@ -52,9 +52,16 @@ def test_setup_from_reference_formats(files):
     filters = list(blob["data"])
     core = syn.random_model("Bu2019lm", filters, seed=0)
     priors, lik = analysis.analysis_setup(_args(dat, prior, "--data-tmax", "14"), svd_mag_model=core)
+    # create_prior_from_args (nmma/em/prior.py:221-244) appends Ebv = DeltaFunction(0) when --use-Ebv is not given
     assert list(priors.keys()) == ["luminosity_distance", "KNphi", "inclination_EM", "timeshift", "log10_mej_dyn",
-                                   "log10_mej_wind"]
-    assert lik.columns == list(priors.keys())
+                                   "log10_mej_wind", "Ebv"]
+    assert priors["Ebv"].peak == 0.0
+    assert lik.columns == list(priors.keys())[:-1]
+    _, lik_e = analysis.analysis_setup(_args(dat, prior, "--data-tmax", "14", "--use-Ebv", "--Ebv-max", "0.4"), svd_mag_model=core)
+    assert lik_e.columns[-1] == "Ebv" and lik_e.priors["Ebv"].maximum == 0.4
+    assert lik_e.priors["Ebv"].prob(0.0) == pytest.approx(2 / 0.4) and lik_e.priors["Ebv"].prob(0.4) == pytest.approx(0.0, abs=1e-12)
+    plan = lik_e.sub_model.plan_layout(lik_e.columns)
+    assert plan["ext"][0] == 1 and plan["ext"][1].col == 6 and np.all(plan["ext"][2] > 1e14)   # P92_SMC_host, nu0 in Hz
     sm = lik.sub_model
     times, mags, errs, trig = sm.light_curve_times, sm.light_curves, sm.light_curve_uncertainties, sm.trigger_time
     assert trig == syn.AT2017GFO_TRIGGER_MJD

@@ -64,3 +64,23 @@ def test_sass_has_tma_and_packed_fma():
     if "Function" not in out:
         out = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in out and "SYNCS" in out and "FFMA2" in out and "LDS.128" in out
+
+
+def test_sass_tensor_core_kernel_is_tcgen05():
+    """The throughput instantiation of the hot path, fused_tc_logl_kernel<10, FAST, unsplit>, really runs on tcgen05:
+    UTCHMMA (tcgen05.mma), LDTM / STTM (tcgen05.ld / st), UTCBAR (tcgen05.commit), UBLKCP (cp.async.bulk), SYNCS
+    (mbarrier) -- and no legacy HMMA / HGMMA.  profiles/r02_sass_fused_tc.txt is the committed histogram."""
+    import shutil
+    import subprocess
+    from nmma_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    blocks = [b for b in re.split(r"\n\s*Function : ", sass) if b.startswith("_ZN4nmma20fused_tc_logl_kernelILi10ELb1ELb0E")]
+    assert len(blocks) == 1, "fused_tc_logl_kernel<10, true, false> not found in the library"
+    body = blocks[0]
+    counts = {op: len(re.findall(r"\b" + op, body)) for op in ("UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "SYNCS")}
+    assert counts["UTCHMMA"] >= 20 and counts["LDTM"] >= 4 and counts["STTM"] >= 8, counts
+    assert counts["UTCBAR"] >= 4 and counts["UBLKCP"] >= 2 and counts["SYNCS"] >= 20, counts
+    assert not re.search(r"\bHMMA|\bHGMMA|\bIMMA", body)
