@@ -1,22 +1,31 @@
 #!/usr/bin/env python
 """Benchmark: kilonova logL evals/sec (Bu2019lm vs AT2017gfo), BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--points M]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--points M] [--configs c3,c4,c5]
 
-A "step" is one pass of the hot path (fused surrogate + likelihood) over one batch of M = 10^6
-prior draws from priors/Bu2019lm.prior per GPU (configs[1] of BASELINE.json; under torchrun every
-rank evaluates its own 10^6-point shard and the logL blocks are all-gathered over NCCL: weak
-scaling, configs[4]).  Weights are random-init of the Bu2019lm architecture (the Zenodo weights
-are not available offline); photometry is the real AT2017gfo table cut at 14 d.
+Headline line (``value`` / ``e2e`` / ``roofline`` / ``cpu_baseline``): BASELINE.json configs[1] -- one "step" is one pass of
+the hot path (fused surrogate + likelihood) over M = 10^6 draws from priors/Bu2019lm.prior per GPU against the real
+AT2017gfo photometry (cut at 14 d), random-init weights of the Bu2019lm architecture (the Zenodo weights are not available
+offline).  Under torchrun every rank evaluates its own 10^6-point block (weak scaling) through
+``nmma_b200.sharding.ShardedEvaluator``; the only collective is the NCCL all-gather of the logL blocks, issued on a side
+stream under the next step's kernels.  ``e2e`` goes through ``EMTransientLikelihood.log_likelihood_batch`` with HOST buffers
+(H2D + kernels + D2H inside the timed region); at N > 1 every rank copies its block into one page-locked shared-memory
+result vector (``HostResultBuffer``) that rank 0 reads in place.
 
-JSON line keys (base contract + tier additions): value (device-resident inputs), e2e (host buffers
-through EMTransientLikelihood.log_likelihood_batch, H2D/D2H inside the timed region), roofline
-(FP32-FMA compute bound; measured FFMA peak as denominator, HBM figures alongside), cpu_baseline
-(the oracle port on the box's host cores, bounded sample), clocks, gpu_launches.
+``config_lines`` carries short runs of the other BASELINE.json configurations in the same JSON line, each with its rate, a
+``roofline`` and an in-run parity check against the CPU oracle:
+  c3  configs[2]  Bu2023Ye-shaped (d = 7) + 4 time-node systematics + the 3 AT2017gfo upper limits + detection limit 24.5
+  c4  configs[3]  Ka2017-shaped sklearn_gp surrogate (Ntr = 329) across ZTF g/r/i + sdssu + PS1 grizy with detection limits
+  c5  configs[4]  10^8 Bu2019lm prior draws made ON the device (Philox, first_index per rank), sharded over the ranks,
+                  one NCCL gather of logL[10^8]
+
+``parity_in_run`` compares rows of the TIMED output (device arm: the last timed step's result, every rank's block of the
+gathered vector; e2e arm: the shared host vector) with the oracle, at every N.
 """
 from __future__ import annotations
 
 import argparse
+import copy
 import json
 import os
 import subprocess
@@ -33,84 +42,138 @@ import numpy as np  # noqa: E402
 METRIC = "kilonova logL evals/sec (Bu2019lm vs AT2017gfo)"
 UNIT = "evals/s"
 WORKLOAD = "Bu2019lm batched likelihood sweep: 10^6 prior draws from priors/Bu2019lm.prior vs AT2017gfo (data_tmax 14 d, 133 obs, 9 filters)"
-N_ROTATE = 6  # distinct input batches cycled between steps: 6 x 48 MB = 288 MB > 126 MB L2
+N_ROTATE = 6      # distinct input batches cycled between steps: 6 x 48 MB = 288 MB > 126 MB L2
+N_PARITY = 256    # rows per rank and configuration compared with the oracle
+SWEEP_TOTAL = 100_000_000
+SWEEP_SEED = 20261018
+
+YAML_TIME = {"config": {"withTime": {"value": True, "filters": [None], "time_nodes": 4, "type": "Uniform", "minimum": 0,
+                                     "maximum": 2},
+                        "withoutTime": {"value": False, "type": "Uniform", "minimum": 0, "maximum": 2}}}
 
 
 # ---------------------------------------------------------------------------------------------
-# workload
+# workloads: one picklable spec per configuration, from which the GPU likelihood and the oracle are both built
 # ---------------------------------------------------------------------------------------------
-def build_workload():
+def make_spec(name):
     from nmma_b200 import synthetic as syn
-    lc_data, filters = syn.load_at2017gfo(data_tmax=14.0)
-    core = syn.random_model("Bu2019lm", filters, seed=0)
-    priors = syn.bu2019lm_prior()
-    return dict(lc_data=lc_data, filters=filters, core=core, priors=priors)
+    from nmma_b200.em import FilterSystematicsHandler
+    if name in ("c2", "c5"):
+        lc_data, filters = syn.load_at2017gfo(data_tmax=14.0)
+        spec = dict(model="Bu2019lm", kind="mlp", filters=filters, core=syn.random_model("Bu2019lm", filters, seed=0),
+                    lc_data=lc_data, priors=syn.bu2019lm_prior(), systematics=None, limit=np.inf,
+                    workload=WORKLOAD if name == "c2" else
+                    f"Bu2019lm {SWEEP_TOTAL:.0e}-point prior-draw sweep, draws made on the device (Philox4x32-10), sharded over the ranks")
+    elif name == "c3":
+        lc_data, filters = syn.load_at2017gfo(data_tmax=14.0)
+        priors = syn.bu2023ye_prior()
+        priors["timeshift"].maximum = 0.1
+        spec = dict(model="Bu2023Ye", kind="mlp", filters=filters, core=syn.random_model("Bu2023Ye", filters, seed=1),
+                    lc_data=lc_data, priors=priors, systematics=copy.deepcopy(YAML_TIME), limit=24.5,
+                    workload="Bu2023Ye-shaped (d = 7) + 4 time-node systematics (legacy YAML withTime) + 3 upper limits + "
+                             "detection limit 24.5 mag vs AT2017gfo")
+    elif name == "c4":
+        filters = ["ztfg", "ztfr", "ztfi", "sdssu", "ps1::g", "ps1::r", "ps1::i", "ps1::z", "ps1::y"]
+        rng = np.random.default_rng(8)
+        times, mags, errs = {}, {}, {}
+        for f in filters:
+            t = np.sort(rng.uniform(0.3, 13.0, 10))
+            e = rng.uniform(0.02, 0.3, 10)
+            e[rng.choice(10, size=2, replace=False)] = np.inf
+            times[f], mags[f], errs[f] = t, 18.0 + 0.15 * t + rng.normal(scale=0.3, size=10), e
+        limits = {"ztfg": 21.7, "ztfr": 21.4, "ztfi": 20.9, "sdssu": 23.9, "ps1::g": 25.0, "ps1::r": 24.7, "ps1::i": 24.0,
+                  "ps1::z": 23.3, "ps1::y": 22.1}
+        priors = syn.ka2017_prior()
+        priors["timeshift"].maximum = 0.2
+        spec = dict(model="Ka2017", kind="gp", filters=filters,
+                    core=syn.random_model("Ka2017", filters, kind="gp", seed=2, Ntr=329),
+                    lc_data=(times, mags, errs, 0.0), priors=priors, systematics=None, limit=limits,
+                    workload="Ka2017-shaped sklearn_gp surrogate (Ntr = 329, K = 10) across ZTF g/r/i + sdssu + PS1 grizy, "
+                             "10 epochs per filter (2 upper limits each), survey detection limits")
+    else:
+        raise ValueError(name)
+    handler = FilterSystematicsHandler(list(spec["filters"]), spec["systematics"], 1.0, spec["lc_data"][0])
+    if spec["systematics"] is not None:
+        handler.setup_systematics_priors(spec["priors"])
+    spec["name"] = name
+    handler.reset(np.asarray(next(iter(spec["core"].values()))["tt"], float), spec["priors"])   # legacy YAML: node times
+    spec["sys_plan"] = handler.device_plan()
+    spec["cols"] = [k for k, p in spec["priors"].items() if not isinstance(p, (int, float)) and not hasattr(p, "peak")]
+    dl = spec["priors"]["luminosity_distance"]
+    from nmma_b200.core.conversion import get_cosmo_grids
+    spec["z_table"] = get_cosmo_grids(dl.minimum, dl.maximum)
+    return spec
 
 
-def gpu_likelihood(wl, device):
+def gpu_likelihood(spec, device):
     from nmma_b200.em import EMTransientLikelihood, FilterSystematicsHandler, SVDLightCurveModel
-    model = SVDLightCurveModel("Bu2019lm", svd_mag_model=wl["core"], interpolation_type="tensorflow",
-                               filters=wl["filters"], device=device)
-    handler = FilterSystematicsHandler(wl["filters"], None, 1.0, wl["lc_data"][0])
-    lik = EMTransientLikelihood(model, wl["lc_data"], handler, wl["priors"], filters=wl["filters"])
-    return lik, model, handler
+    itype = "sklearn_gp" if spec["kind"] == "gp" else "tensorflow"
+    model = SVDLightCurveModel(spec["model"], svd_mag_model=spec["core"], interpolation_type=itype,
+                               filters=list(spec["filters"]), device=device)
+    handler = FilterSystematicsHandler(list(spec["filters"]), spec["systematics"], 1.0, spec["lc_data"][0])
+    lik = EMTransientLikelihood(model, spec["lc_data"], handler, spec["priors"], filters=list(spec["filters"]),
+                                detection_limit=spec["limit"])
+    assert lik.columns == spec["cols"], (lik.columns, spec["cols"])
+    return lik
 
 
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle (a port of the reference's per-point Python path) on the host cores
 # ---------------------------------------------------------------------------------------------
-_W = {}
+_SPECS = {}      # inherited by the forked workers
+_ORACLES = {}
 
 
-def _cpu_init(wl_blob):
+def _cpu_init():
     try:
         from threadpoolctl import threadpool_limits
-        _W["tl"] = threadpool_limits(1)          # NMMA pins BLAS threads to 1 for pooled runs (joint/main.py:2)
+        _ORACLES["_tl"] = threadpool_limits(1)          # NMMA pins BLAS threads to 1 for pooled runs (joint/main.py:2)
     except Exception:  # noqa: BLE001
         pass
     import warnings
     warnings.filterwarnings("ignore")
-    from nmma_b200.em.model import model_parameters_dict
-    from oracle import harness
-    wl = wl_blob
-    tt = next(iter(wl["core"].values()))["tt"]
-    lik, fixed = harness.build_oracle_likelihood(
-        wl["core"], model_parameters_dict["Bu2019lm"], wl["filters"], np.asarray(tt, float), wl["filters"],
-        wl["lc_data"], wl["priors"], sys_plan=None, error_budget=1.0, z_table=wl["z_table"])
-    _W["lik"], _W["fixed"], _W["cols"] = lik, fixed, wl["cols"]
 
 
-def _cpu_eval(chunk):
+def _oracle_for(name):
+    if name not in _ORACLES:
+        from nmma_b200.em.model import model_parameters_dict
+        from oracle import harness
+        s = _SPECS[name]
+        tt = next(iter(s["core"].values()))["tt"]
+        _ORACLES[name] = harness.build_oracle_likelihood(
+            harness.oracle_ready_core(s["core"]), model_parameters_dict[s["model"]], s["filters"], np.asarray(tt, float),
+            s["filters"], s["lc_data"], s["priors"], sys_plan=s["sys_plan"], detection_limit=s["limit"],
+            z_table=s["z_table"])
+    return _ORACLES[name]
+
+
+def _cpu_eval(task):
     from oracle import harness
-    return harness.oracle_logl(_W["lik"], _W["fixed"], chunk, _W["cols"])
+    name, chunk = task
+    lik, fixed = _oracle_for(name)
+    return harness.oracle_logl(lik, fixed, chunk, _SPECS[name]["cols"])
 
 
 class CpuArm:
     """multiprocessing pool over the host cores (the analogue of the reference's schwimmbad task farm,
     nmma/core/mpi_setup.py:651-683); workers are forked before CUDA is initialised."""
 
-    def __init__(self, wl, cols, z_table, cores=None):
+    def __init__(self, cores=None):
         import multiprocessing as mp
         self.cores = cores or len(os.sched_getaffinity(0))
-        blob = dict(wl)
-        blob["cols"], blob["z_table"] = cols, z_table
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(blob,))
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init)
 
-    def run(self, pts):
-        chunks = np.array_split(pts, self.cores * 4)
+    def run(self, name, pts, parts=None):
+        if len(pts) == 0:
+            return np.zeros(0), 0.0
+        chunks = np.array_split(pts, min(len(pts), parts or self.cores * 4))
         t0 = time.perf_counter()
-        out = np.concatenate(self.pool.map(_cpu_eval, chunks))
+        out = np.concatenate(self.pool.map(_cpu_eval, [(name, c) for c in chunks]))
         return out, time.perf_counter() - t0
 
     def close(self):
         self.pool.close()
         self.pool.join()
-
-
-def z_table_for(priors):
-    from nmma_b200.core.conversion import get_cosmo_grids
-    dl = priors["luminosity_distance"]
-    return get_cosmo_grids(dl.minimum, dl.maximum)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -162,73 +225,131 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------
 def reference_arm(args):
-    """The reference's own CPU implementation of the path (oracle port; the real package cannot be
-    imported offline -- DESIGN.md) on all host cores; each step is a bounded sample of the workload."""
+    """The reference's own CPU implementation of the path on all host cores; each step is a bounded sample of the
+    workload.  The real package cannot be imported offline (bilby, sncosmo, astropy, tensorflow absent -- DESIGN.md), so the
+    per-point path runs through the oracle PORT (same NumPy / SciPy / sklearn calls, fp32 NumPy MLP standing in for the
+    Keras call); the port reproduces the reference's own source files to 1e-15 on the committed vectors
+    (tests/test_reference_vectors.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = build_workload()
-    cols = [k for k in wl["priors"].keys()]
-    arm = CpuArm(wl, cols, z_table_for(wl["priors"]))
+    _SPECS["c2"] = make_spec("c2")
+    spec = _SPECS["c2"]
+    arm = CpuArm()
     rng = np.random.default_rng(1234)
-    probe, _ = wl["priors"].sample_array(arm.cores * 40, rng, cols)
-    _, dt = arm.run(probe)
+    probe, _ = spec["priors"].sample_array(arm.cores * 40, rng, spec["cols"])
+    _, dt = arm.run("c2", probe)
     rate = len(probe) / dt
     # bounded sample: ~4 s of CPU work per step, shrunk so that steps + warm-up stay within ~2 minutes whatever K is
     sec_per_step = min(4.0, max(0.2, 120.0 / max(1, args.steps + args.warmup)))
     per_step = int(max(arm.cores * 40, min(rate * sec_per_step, 200000)))
-    pts, _ = wl["priors"].sample_array(per_step, rng, cols)
+    pts, _ = spec["priors"].sample_array(per_step, rng, spec["cols"])
     for _ in range(args.warmup):
-        arm.run(pts)
+        arm.run("c2", pts)
     t = 0.0
     for _ in range(args.steps):
-        _, dt = arm.run(pts)
+        _, dt = arm.run("c2", pts)
         t += dt
     arm.close()
     value = per_step * args.steps / t
-    sample = f"{per_step} prior draws per step through the per-point Python path (NumPy/SciPy oracle port, fp32 NumPy MLP standing in for Keras)"
+    sample = (f"{per_step} prior draws per step through the per-point Python path (NumPy/SciPy oracle port of the reference, "
+              "fp32 NumPy MLP standing in for Keras), multiprocessing pool on all host cores")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 MLP / f64 likelihood", "data": "synthetic weights, real AT2017gfo photometry",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 MLP / f64 likelihood",
+        "data": "synthetic weights, real AT2017gfo photometry",
         "config": {"workload": WORKLOAD, "points_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def rel_err(got, ref):
+    got, ref = np.asarray(got, float), np.asarray(ref, float)
+    if got.shape != ref.shape:
+        return float("inf"), False
+    sent = -1.7976931348623157e308
+    masks_equal = bool(np.array_equal(got == sent, ref == sent))
+    ok = ref != sent
+    if not ok.any() or not masks_equal:
+        return (0.0 if masks_equal else float("inf")), masks_equal
+    return float((np.abs(got[ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))).max()), masks_equal
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
+    from nmma_b200.sharding import HostResultBuffer, ShardedEvaluator, shard_bounds
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     M = args.points
-    wl = build_workload()
-    cols = [k for k in wl["priors"].keys()]
-    ztab = z_table_for(wl["priors"])
+    wanted = [c for c in args.configs.split(",") if c]
+    names = ["c2"] + [c for c in ("c3", "c4", "c5") if c in wanted]
+    for n in names:
+        _SPECS[n] = make_spec(n)
+    sizes = {"c2": M, "c3": args.points_c3, "c4": args.points_c4}
 
-    # ---- CPU baseline first (fork before CUDA init), rank 0 at N = 1 only ----
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        arm = CpuArm(wl, cols, ztab)
-        rng = np.random.default_rng(99)
-        probe, _ = wl["priors"].sample_array(arm.cores * 40, rng, cols)
-        _, dt = arm.run(probe)
-        n_s = int(max(arm.cores * 40, min(len(probe) / dt * 12.0, 400000)))      # ~12 s of CPU work
-        cpu_pts, _ = wl["priors"].sample_array(n_s, rng, cols)
-        cpu_ref, dt = arm.run(cpu_pts)
-        one_core_pts = cpu_pts[:300]
-        _cpu_init(dict(wl, cols=cols, z_table=ztab))
-        t0 = time.perf_counter()
-        _cpu_eval(one_core_pts)
-        one_core = len(one_core_pts) / (time.perf_counter() - t0)
+    # ---- inputs: rank r draws its blocks with seed 1234 + r; the first N_PARITY rows of the LAST timed batch are the
+    # parity rows (every rank can rebuild every other rank's parity rows, rank 0 scores them with the oracle) ----
+    def batches_for(name, r, count, n):
+        s = _SPECS[name]
+        rng = np.random.default_rng(1234 + 1000 * list(_SPECS).index(name) + r)
+        return [s["priors"].sample_array(n, rng, s["cols"])[0] for _ in range(count)]
+
+    def parity_rows(name, r, n):
+        s = _SPECS[name]
+        rng = np.random.default_rng(777 + 1000 * list(_SPECS).index(name) + r)
+        return s["priors"].sample_array(n, rng, s["cols"])[0]
+
+    n_par = {"c2": N_PARITY, "c3": N_PARITY, "c4": 16, "c5": 64}
+
+    # ---- CPU work first (fork before CUDA init), rank 0 only ----
+    cpu, oracle_ref = None, {}
+    if rank == 0:
+        arm = CpuArm()
+        if world == 1 and not args.no_cpu:
+            s = _SPECS["c2"]
+            rng = np.random.default_rng(99)
+            probe, _ = s["priors"].sample_array(arm.cores * 40, rng, s["cols"])
+            _, dt = arm.run("c2", probe)
+            n_s = int(max(arm.cores * 40, min(len(probe) / dt * 12.0, 400000)))      # ~12 s of CPU work
+            cpu_pts, _ = s["priors"].sample_array(n_s, rng, s["cols"])
+            _, dt = arm.run("c2", cpu_pts)
+            t0 = time.perf_counter()
+            arm.run("c2", cpu_pts[:300], parts=1)
+            one_core = 300 / (time.perf_counter() - t0)
+            cpu = {"value": n_s / dt, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                   "sample": f"{n_s} draws of the same prior through the per-point NumPy/SciPy oracle port of the reference "
+                             f"(fp32 NumPy MLP standing in for Keras), multiprocessing pool on all host cores",
+                   "one_core_value": one_core, "cpu_count": os.cpu_count()}
+        for name in names:
+            if name == "c5":
+                continue
+            pts = np.concatenate([parity_rows(name, r, n_par[name]) for r in range(world)])
+            oracle_ref[name] = arm.run(name, pts)[0].reshape(world, -1)
+        if "c5" in names:
+            from oracle import philox as ph
+            s = _SPECS["c5"]
+            kinds, params, tables = s["priors"].device_plan(s["cols"])
+            kind_names = {0: "Uniform", 1: "DeltaFunction", 2: "Sine", 3: "Cosine", 4: "Gaussian", 5: "TruncatedGaussian",
+                          6: "PowerLaw", 7: "Triangular", 8: "Interped"}
+            blocks = []
+            for r in range(world):
+                lo, hi = shard_bounds(args.sweep_total, world, r)
+                first = lo + (hi - lo) // 3        # well inside the shard, not at its head
+                u = ph.unit_cube(SWEEP_SEED, first, n_par["c5"], len(s["cols"]))
+                blocks.append(np.stack([ph.rescale_column(kind_names[int(k)], params[j], u[:, j], tables.get(j))
+                                        for j, k in enumerate(kinds)], axis=1))
+            oracle_ref["c5"] = arm.run("c5", np.concatenate(blocks))[0].reshape(world, -1)
         arm.close()
-        cpu = {"value": n_s / dt, "unit": UNIT, "cores": arm.cores, "kind": "port",
-               "sample": f"{n_s} of the same prior draws through the per-point NumPy/SciPy oracle port "
-                         f"(fp32 NumPy MLP standing in for Keras), multiprocessing pool on all host cores",
-               "one_core_value": one_core, "cpu_count": os.cpu_count()}
 
     # nvidia-smi needs ~1 s to start: launch it now, keep the samples that fall inside the timed regions
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -236,174 +357,295 @@ def gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     dev = torch.device(f"cuda:{local_rank}")
-    lik, model, handler = gpu_likelihood(wl, local_rank)
-    eng = lik.sub_model.engine_for(cols)
-    if args.path:
-        eng.set_option("path", args.path)
-    if args.packed is not None:
-        eng.set_option("packed_fma", args.packed)
-    if args.pt is not None:
-        eng.set_option("points_per_thread", args.pt)
-
-    rng = np.random.default_rng(1234 + rank)
-    host_batches = []
-    for _ in range(N_ROTATE):
-        p, _ = wl["priors"].sample_array(M, rng, cols)
-        host_batches.append(torch.from_numpy(p).pin_memory())
-    dev_batches = [b.to(dev) for b in host_batches]
-    out_local = torch.empty(M, dtype=torch.float64, device=dev)
-    out_all = torch.empty(M * world, dtype=torch.float64, device=dev) if world > 1 else out_local
-    out_host = torch.empty(M * world if rank == 0 else 1, dtype=torch.float64).pin_memory()
-
-    # parity spot check against the CPU oracle inside the same run
-    parity = None
-    if cpu is not None:
-        got = lik.log_likelihood_batch(cpu_pts[:2000], cols)
-        err = np.abs(got - cpu_ref[:2000]) / np.maximum(1.0, np.abs(cpu_ref[:2000]))
-        parity = {"points": 2000, "max_rel_err": float(err.max()), "tolerance": 1e-4}
-        assert err.max() < 1e-4, f"GPU/CPU logL disagree: {err.max()}"
-
-    ffma = None
-    if rank == 0:
-        ffma = {"scalar_tflops": eng.ffma_peak(0, 20000) / 1e12, "packed_tflops": eng.ffma_peak(1, 20000) / 1e12}
-
-    def step_device(i):
-        eng.logl_device(dev_batches[i % N_ROTATE], out=out_local)
-        if world > 1:
-            dist.all_gather_into_tensor(out_all, out_local)
-
-    def step_e2e(i):
-        hb = host_batches[i % N_ROTATE]
-        if world == 1:
-            lik.log_likelihood_batch(hb.numpy(), cols, out=out_host.numpy())
-        else:
-            eng.logl_host(hb.numpy(), out=out_local)       # pipelined H2D + kernels, result stays on the device
-            dist.all_gather_into_tensor(out_all, out_local)
-            if rank == 0:
-                out_host.copy_(out_all, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+    sh = ShardedEvaluator(lambda p: None) if world > 1 else None
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, per_launch=False):
-        for i in range(warmup):
-            fn(i)
-        sync()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            if per_launch:
-                evs[i][0].record()
-            fn(warmup + i)
-            if per_launch:
-                evs[i][1].record()
-        e1.record()
-        sync()
-        t1 = time.perf_counter()
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        per = [a.elapsed_time(b) for a, b in evs] if per_launch else None
-        return float(t.item()), per, (t0, t1)
+        return float(t.item())
 
-    l0 = eng.get_info("launches")
-    ms_total, per_launch, (w0, w1) = timed(step_device, args.steps, args.warmup, per_launch=True)
-    launches = eng.get_info("launches") - l0 - args.warmup
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
 
-    # e2e: wall-clock inside the C call includes the copies; device events would miss the host part
-    for i in range(max(args.warmup, 3)):
-        step_e2e(i)
-    sync()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(i)
-    sync()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    def run_config(name, steps, warmup, with_e2e):
+        """Device-timed weak-scaled run of one configuration (+ optional e2e arm); returns a dict for the JSON line."""
+        spec = _SPECS[name]
+        cols, P = spec["cols"], len(spec["cols"])
+        n = sizes[name]
+        lik = gpu_likelihood(spec, local_rank)
+        eng = lik.sub_model.engine_for(cols)
+        if name == "c2" and args.path:
+            eng.set_option("path", args.path)
+        nrot = N_ROTATE if n * P * 8 * N_ROTATE > 130e6 else max(N_ROTATE, int(260e6 / (n * P * 8)) + 1)
+        host = batches_for(name, rank, nrot, n)
+        last = (warmup + steps - 1) % nrot
+        host[last][:n_par[name]] = parity_rows(name, rank, n_par[name])
+        host_t = [torch.from_numpy(b).pin_memory() for b in host]
+        dev_t = [b.to(dev) for b in host_t]
+        local_bufs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(2)]
+        full_bufs = [torch.empty(n * world, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else local_bufs
+
+        def step_device(i):
+            if world == 1:
+                eng.logl_device(dev_t[i % nrot], out=local_bufs[i % 2])
+                return i % 2
+            return sh.gather_overlapped(lambda out: eng.logl_device(dev_t[i % nrot], out=out), local_bufs, full_bufs, i)
+
+        for i in range(warmup):
+            step_device(i)
+        if sh:
+            sh.drain()
+        sync()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.get_info("launches")
+        w0 = time.perf_counter()
+        e0.record()
+        slot = 0
+        for i in range(steps):
+            evs[i][0].record()
+            slot = step_device(warmup + i)
+            evs[i][1].record()       # on the compute stream: kernel time only, the overlapped gather is not inside
+        if sh:
+            sh.drain()
+        e1.record()
+        sync()
+        w1 = time.perf_counter()
+        launches = eng.get_info("launches") - l0
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        # parity on the timed output: the parity rows head every rank's block of the last step's gathered vector
+        parity = None
+        got = full_bufs[slot].view(world, n)[:, :n_par[name]].cpu().numpy() if world > 1 else \
+            local_bufs[slot][:n_par[name]].cpu().numpy()[None, :]
+        if rank == 0:
+            err, masks = rel_err(got, oracle_ref[name])
+            parity = {"rows": int(got.size), "ranks_checked": world, "max_rel_err": err, "sentinel_masks_equal": masks,
+                      "tolerance": 1e-4, "what": "rows of the last TIMED step's output (all ranks' blocks of the gathered vector)"}
+            assert masks and err < 1e-4, f"{name}: GPU/oracle disagree on the timed output: {err}"
+        res = {"ms_total": ms_total, "kern_ms": kern_ms, "launches": int(launches), "parity": parity, "window": (w0, w1),
+               "n": n, "P": P, "eng": eng, "lik": lik, "nrot": nrot}
+        if with_e2e:
+            hb = None
+            if world > 1:
+                hb = HostResultBuffer(n * world, rank, world, name=f"nmma_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{name}")
+                dist.barrier()
+                hb.attach()
+                out_np = hb.local
+            else:
+                out_host = torch.empty(n, dtype=torch.float64).pin_memory()
+                out_np = out_host.numpy()
+
+            def step_e2e(i):
+                lik.log_likelihood_batch(host_t[i % nrot].numpy(), cols, out=out_np)   # H2D + kernels + D2H, synchronised
+                if world > 1:
+                    dist.barrier()          # the host consumer (rank 0) sees the complete vector after every step
+
+            for i in range(max(warmup, 3)):
+                step_e2e(i)
+            sync()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                step_e2e(warmup + i)
+            sync()
+            e2e_s = max_over_ranks(time.perf_counter() - t0)
+            res["window"] = (w0, time.perf_counter())
+            pe = None
+            if rank == 0:
+                full = hb.full.reshape(world, n)[:, :n_par[name]] if world > 1 else out_np[None, :n_par[name]]
+                err, masks = rel_err(np.array(full), oracle_ref[name])
+                pe = {"rows": int(full.size), "max_rel_err": err, "sentinel_masks_equal": masks,
+                      "what": "rows of the host result vector after the last timed e2e step (all ranks' slices)"}
+                assert masks and err < 1e-4, f"{name}: e2e output disagrees with the oracle: {err}"
+            if hb is not None:
+                dist.barrier()
+                hb.close()
+            res["e2e_s"], res["parity_e2e"] = e2e_s, pe
+        return res
+
+    def roofline_for(name, r):
+        eng, n = r["eng"], r["n"]
+        flop = eng.get_info("algorithmic_flop_per_eval")
+        achieved = n * flop / (r["kern_ms"] * 1e-3) / 1e12
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_gbs = n * (r["P"] * 8 + 8) / (r["kern_ms"] * 1e-3) / 1e9
+        out = {"algorithmic_flop_per_eval": flop, "kernel_ms_per_launch": r["kern_ms"],
+               "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
+                       "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}}
+        path = eng.get_info("last_path")
+        if _SPECS[name]["kind"] == "gp":
+            out.update({"bound": "fp64 (CUDA cores: F K Ntr kernel values (1 + r^2 q)^-alpha per evaluation)",
+                        "achieved": achieved, "peak": pk["dfma"], "unit": "TFLOP/s", "frac": achieved / pk["dfma"],
+                        "peak_source": "fp64 FMA micro-benchmark measured in this run (nmma_b200_dfma_peak)",
+                        "kernel": "gp_logl_kernel" if eng.get_info("last_path") == 4 else "coeff_gp_kernel + backend_logl_kernel"})
+        elif path == 3:
+            executed = eng.get_info("tc_executed_flop_per_eval")
+            out.update({"bound": "tensor", "achieved": achieved, "peak": pk["tf32"], "unit": "TFLOP/s",
+                        "frac": achieved / pk["tf32"],
+                        "peak_source": "dense tcgen05 kind::tf32 rate measured in this run (nmma_b200_tf32_peak: 128x128x8 MMAs, "
+                                       "A in TMEM, every SM); MEASURED_PEAKS.json holds bf16 only",
+                        "bf16_tflops_measured_peaks_json": peaks.get("bf16_tflops"),
+                        "executed_tensor_tflops": n * executed / (r["kern_ms"] * 1e-3) / 1e12,
+                        "executed_frac_of_tf32_peak": n * executed / (r["kern_ms"] * 1e-3) / 1e12 / pk["tf32"],
+                        "executed_tensor_flop_per_eval": executed, "frac_of_ffma_peak": achieved / pk["ffma"],
+                        "kernel": "fused_tc_logl_kernel (tcgen05 3xTF32 split)"})
+        else:
+            out.update({"bound": "fp32_fma (CUDA cores)", "achieved": achieved, "peak": pk["ffma"], "unit": "TFLOP/s",
+                        "frac": achieved / pk["ffma"], "peak_source": "FFMA micro-benchmark measured in this run",
+                        "kernel": {1: "fused_mlp_logl_kernel (FFMA)", 2: "two-stage kernels"}.get(path, "?")})
+        return out
+
+    # ---- headline configuration ----
+    main = run_config("c2", args.steps, args.warmup, with_e2e=True)
+    eng = main["eng"]
+    pk = {"ffma": max(eng.ffma_peak(0, 20000), eng.ffma_peak(1, 20000)) / 1e12, "dfma": eng.dfma_peak(20000) / 1e12,
+          "tf32": eng.tf32_peak(20000) / 1e12}
+    window = main["window"]
+
+    # ---- the other BASELINE.json configurations (short runs) ----
+    config_lines = {}
+    for name in names[1:]:
+        if name == "c5":
+            continue
+        r = run_config(name, args.steps_cfg, 3, with_e2e=False)
+        if rank == 0:
+            n = r["n"]
+            config_lines[name] = {
+                "workload": _SPECS[name]["workload"], "value": n * world * args.steps_cfg / (r["ms_total"] * 1e-3), "unit": UNIT,
+                "scaling": "weak", "points_per_gpu_per_step": n, "steps": args.steps_cfg, "ms_per_step": r["ms_total"] / args.steps_cfg,
+                "P": r["P"], "gpu_launches": r["launches"], "roofline": roofline_for(name, r), "parity_in_run": r["parity"],
+                "l2": f"{r['nrot']} rotating input batches"}
+        del r
+
+    if "c5" in names:
+        spec = _SPECS["c5"]
+        cols = spec["cols"]
+        lik5 = main["lik"]                       # same likelihood as c2: the sweep adds the on-device prior draws
+        total = args.sweep_total
+        lo, hi = shard_bounds(total, world, rank)
+        out_local = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+        out_full = torch.empty(total, dtype=torch.float64, device=dev) if world > 1 else out_local
+        eng5 = lik5.sub_model.engine_for(cols)
+
+        def sweep_once():
+            eng5.logl_sweep(hi - lo, seed=SWEEP_SEED, first_index=lo, out=out_local)
+            if world > 1:
+                sh.gather(out_local, n_global=total, out=out_full)
+
+        sweep_once()                              # warm-up pass over a short prefix would not warm the allocator: full pass
+        sync()
+        l0 = eng5.get_info("launches")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sweep_once()
+        e1.record()
+        sync()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches5 = eng5.get_info("launches") - l0
+        got = []
+        for r_ in range(world):
+            rlo, rhi = shard_bounds(total, world, r_)
+            first = rlo + (rhi - rlo) // 3
+            got.append(out_full[first:first + n_par["c5"]].cpu().numpy())
+        finite = int(torch.isfinite(out_full).sum().item()) if rank == 0 else 0
+        if rank == 0:
+            err, masks = rel_err(np.stack(got), oracle_ref["c5"])
+            assert masks and err < 1e-4, f"c5: sharded sweep disagrees with the oracle: {err}"
+            rate = total / (ms * 1e-3)
+            flop = eng5.get_info("algorithmic_flop_per_eval")
+            config_lines["c5"] = {
+                "workload": spec["workload"], "value": rate, "unit": UNIT, "scaling": "strong", "total_points": total,
+                "ms_per_sweep": ms, "points_per_gpu": hi - lo, "gpu_launches": int(launches5),
+                "collective": f"one ncclAllGather of logL[{total}] ({total * 8 / 1e6:.0f} MB) after the sweep" if world > 1 else "none (1 GPU)",
+                "h2d_bytes": 0, "d2h_bytes": 0, "finite_rows": finite,
+                "roofline": {"bound": "tensor", "achieved": rate / world * flop / 1e12, "peak": pk["tf32"], "unit": "TFLOP/s",
+                             "frac": rate / world * flop / 1e12 / pk["tf32"], "per": "GPU, draws + gather inside the timed region",
+                             "peak_source": "nmma_b200_tf32_peak measured in this run"},
+                "parity_in_run": {"rows": int(np.stack(got).size), "ranks_checked": world, "max_rel_err": err,
+                                  "sentinel_masks_equal": masks, "tolerance": 1e-4,
+                                  "what": "rows of the TIMED gathered sweep output at 1/3 of every rank's shard vs the oracle on "
+                                          "the same Philox draws rebuilt on the CPU (oracle/philox.py)"}}
+
+    # ---- one-point latency through the bilby seam (pymultinest-style sampler: one dict per call) ----
+    latency = None
+    if rank == 0:
+        lik = main["lik"]
+        cols = _SPECS["c2"]["cols"]
+        row = parity_rows("c2", 0, 8)
+        dicts = [dict(zip(cols, r_)) for r_ in row]
+        for d in dicts:
+            lik.log_likelihood(d)
+        t0 = time.perf_counter()
+        reps = 400
+        for i in range(reps):
+            lik.log_likelihood(dicts[i % 8])
+        dt = (time.perf_counter() - t0) / reps
+        latency = {"us_per_call": dt * 1e6, "evals_per_s": 1.0 / dt, "api": "EMTransientLikelihood.log_likelihood(dict), N = 1",
+                   "cpu_one_core_evals_per_s": cpu["one_core_value"] if cpu else None}
+
     w2 = time.perf_counter()
     clocks = None
     if sampler:
-        clocks = sampler.stop(w0, w2)          # device-timed loop + e2e loop, both under load
+        clocks = sampler.stop(window[0], window[1])
         if clocks is not None:
-            clocks["window"] = "device-timed steps and e2e steps (contiguous, GPU busy throughout)"
+            clocks["window"] = "device-timed steps and e2e steps of the headline configuration (contiguous, GPU busy throughout)"
 
     if rank == 0:
         total_pts = M * world
-        value = total_pts * args.steps / (ms_total * 1e-3)
-        flop = eng.get_info("algorithmic_flop_per_eval")
-        last_path = eng.get_info("last_path")
-        kern_ms = float(np.mean(per_launch))
-        achieved = M * flop / (kern_ms * 1e-3) / 1e12
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        P = main["P"]
+        value = total_pts * args.steps / (main["ms_total"] * 1e-3)
+        roofline = roofline_for("c2", main)
+        roofline["ffma_peak_measured_tflops"] = pk["ffma"]
+        roofline["dfma_peak_measured_tflops"] = pk["dfma"]
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             pass
-        P = len(cols)
-        ffma_peak = max(ffma["scalar_tflops"], ffma["packed_tflops"])
-        hbm = {"achieved_gbs": M * (P * 8 + 8) / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-               "frac": M * (P * 8 + 8) / (kern_ms * 1e-3) / 1e9 / hbm_peak,
-               "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}
-        if last_path == 3:
-            # tensor-core kernel: tcgen05 kind::tf32 runs at half the bf16 rate (tools/tc_probe.cu: 128*N/256 cycles per
-            # K=8 MMA = 4096 FLOP/clk/SM); the 3xTF32 split and the N=16 / K=8 operand padding make the EXECUTED
-            # tensor FLOPs 4.79x the algorithmic ones -- both are reported, `achieved` stays algorithmic.
-            bf16_peak = peaks.get("bf16_tflops", 1650.0)
-            tf32_peak = bf16_peak / 2.0
-            executed = eng.get_info("tc_executed_flop_per_eval")
-            roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                        "frac": achieved / tf32_peak,
-                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops / 2 (dense tf32 = half the bf16 rate)" if peaks
-                                        else "fallback 1650 bf16 TFLOP/s / 2"),
-                        "executed_tensor_tflops": M * executed / (kern_ms * 1e-3) / 1e12,
-                        "executed_frac_of_tf32_peak": M * executed / (kern_ms * 1e-3) / 1e12 / tf32_peak,
-                        "executed_tensor_flop_per_eval": executed,
-                        "frac_of_ffma_peak": achieved / ffma_peak}
-        else:
-            roofline = {"bound": "fp32_fma (CUDA cores; neither HBM nor tensor: SURVEY.md 8d)",
-                        "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s", "frac": achieved / ffma_peak,
-                        "peak_source": "FFMA micro-benchmark measured in this run (nmma_b200_ffma_peak); nominal 74.4 TFLOP/s at 1965 MHz",
-                        "frac_of_nominal": achieved / 74.4}
-        roofline.update({"ffma_peak_measured": ffma, "algorithmic_flop_per_eval": flop, "kernel_ms_per_launch": kern_ms,
-                         "hbm": hbm, "traffic": traffic})
-        kname = {1: "fused_mlp_logl_kernel (FFMA)", 2: "two_stage", 3: "fused_tc_logl_kernel (tcgen05 3xTF32)"}.get(last_path, "?")
+        roofline["traffic"] = traffic
+        last_path = eng.get_info("last_path")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": main["ms_total"] / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 MLP (3xTF32 split on tcgen05) / f64 likelihood" if last_path == 3 else "f32 MLP (FFMA) / f64 likelihood",
             "data": "synthetic: random-init Bu2019lm-shaped weights, real AT2017gfo photometry",
             "config": {"workload": WORKLOAD, "points_per_gpu_per_step": M, "global_points_per_step": total_pts,
-                       "sharding": f"contiguous row blocks x{world}, NCCL all-gather of logL" if world > 1 else "single GPU",
+                       "sharding": (f"contiguous row blocks x{world} (ShardedEvaluator), NCCL all-gather of logL on a side stream "
+                                    f"under the next step's kernels") if world > 1 else "single GPU",
                        "l2": f"inputs rotate through {N_ROTATE} distinct batches ({N_ROTATE * M * P * 8 / 1e6:.0f} MB > 126 MB L2)",
-                       "kernel_path": kname},
-            "e2e": {"value": total_pts * args.steps / e2e_s, "unit": UNIT,
+                       "kernel_path": roofline.get("kernel")},
+            "e2e": {"value": total_pts * args.steps / main["e2e_s"], "unit": UNIT,
                     "h2d_bytes_per_step": total_pts * P * 8, "d2h_bytes_per_step": total_pts * 8,
-                    "api": "EMTransientLikelihood.log_likelihood_batch -> nmma_b200_logl_host (pinned host buffers)"},
-            "gpu_launches": int(launches),
+                    "api": "EMTransientLikelihood.log_likelihood_batch -> nmma_b200_logl_host (pinned host buffers)" +
+                           ("; every rank's D2H lands in its slice of one page-locked shared-memory vector read by rank 0 "
+                            "(HostResultBuffer), no collective" if world > 1 else ""),
+                    "parity_in_run": main["parity_e2e"]},
+            "gpu_launches": main["launches"],
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "parity_in_run": parity,
+            "parity_in_run": main["parity"],
+            "config_lines": config_lines,
+            "latency_one_point": latency,
+            "wall_s": {"total": w2 - T_START},
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+T_START = time.perf_counter()
 
 
 def main():
@@ -413,9 +655,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--configs", type=str, default="c3,c4,c5", help="extra BASELINE.json configurations to run (config_lines)")
+    ap.add_argument("--steps-cfg", dest="steps_cfg", type=int, default=10)
+    ap.add_argument("--points-c3", dest="points_c3", type=int, default=1_000_000)
+    ap.add_argument("--points-c4", dest="points_c4", type=int, default=200_000)
+    ap.add_argument("--sweep-total", dest="sweep_total", type=int, default=SWEEP_TOTAL)
     ap.add_argument("--path", type=int, default=0)
-    ap.add_argument("--packed", type=int, default=None)
-    ap.add_argument("--pt", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -76,6 +76,35 @@ def build_oracle_likelihood(core, model_parameters, model_filters, sample_times,
     return lik, fixed
 
 
+class UnpackedGP:
+    """Oracle-side stand-in for a fitted sklearn GaussianProcessRegressor rebuilt from unpacked arrays:
+    ``predict`` follows sklearn's ``kernel_(X, X_train_) @ alpha_`` with RationalQuadratic.__call__
+    (cdist(X/l, Y/l, 'sqeuclidean'); base = 1 + d/(2 alpha); K = C^2 * base**-alpha)."""
+
+    def __init__(self, X, alpha, c2, ra, rl, ym, ys):
+        self.X, self.alpha, self.c2, self.ra, self.rl, self.ym, self.ys = X, alpha, c2, ra, rl, ym, ys
+
+    def predict(self, x, return_std=False):
+        from scipy.spatial.distance import cdist
+        d = cdist(np.atleast_2d(x) / self.rl, self.X / self.rl, metric="sqeuclidean")
+        K = self.c2 * (1 + d / (2 * self.ra)) ** (-self.ra)
+        y = self.ys * (K @ self.alpha) + self.ym
+        return (y, np.zeros_like(y)) if return_std else y
+
+
+def oracle_ready_core(core):
+    """Replace unpacked GP dicts by objects with a ``predict`` method for the oracle."""
+    out = {}
+    for f, e in core.items():
+        e = dict(e)
+        if isinstance(e.get("gps"), dict):
+            g = e["gps"]
+            e["gps"] = [UnpackedGP(g["X"], g["alpha"][i], g["c2"][i], g["rq_alpha"][i], g["rq_len"][i],
+                                   g["ymean"][i], g["ystd"][i]) for i in range(g["alpha"].shape[0])]
+        out[f] = e
+    return out
+
+
 def oracle_logl(lik, fixed, points, columns):
     out = np.empty(len(points))
     for i, row in enumerate(np.asarray(points, float)):

@@ -178,7 +178,7 @@ def test_mlp_fp32_accuracy_vs_fp64_truth(torch_cuda):
     eng = model._canonical_engine(np.asarray(model.model_times, float))
     rng = np.random.default_rng(2)
     x = rng.uniform([-2.0, -2.0, 0.0], [-1.05, -1.05, 90.0], size=(256, 3))
-    pts = np.concatenate([x, np.full((256, 1), 40.0), np.zeros((256, 2))], axis=1)
+    pts = np.concatenate([x, np.full((256, 1), 40.0), np.zeros((256, 3))], axis=1)   # [x, dL, timeshift, redshift, Ebv]
     got = eng.coeffs(pts).cpu().numpy()
     for fi, f in enumerate(filters):
         W1, b1, W2, b2 = core[f]["model"]
