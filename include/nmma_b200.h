@@ -125,10 +125,13 @@ int nmma_b200_set_sample_grid(nmma_b200_t* h, int S, const double* sample_times)
  * combine_lc_params, nmma/em/model.py:272-303,701-705. */
 int nmma_b200_set_param_layout(nmma_b200_t* h, int P,
                                const nmma_b200_param_src* model_params /* d, model order */,
-                               nmma_b200_param_src luminosity_distance /* default const 1e-5 */,
-                               nmma_b200_param_src timeshift /* default const 0 */,
-                               nmma_b200_param_src redshift /* used when z_mode == Z_PARAM */,
+                               const nmma_b200_param_src* luminosity_distance /* NULL: const 1e-5 Mpc (10 pc) */,
+                               const nmma_b200_param_src* timeshift /* NULL: const 0 */,
+                               const nmma_b200_param_src* redshift /* read when z_mode == Z_PARAM; NULL: const 0 */,
                                int z_mode);
+/* The three scalars are passed by pointer, not by value: a {int32, int32, double} struct by value is split over an
+ * integer and an SSE register, and ctypes/libffi (CPython 3.12) hands every such argument the LAST struct's double --
+ * a binder would silently evaluate at the wrong distance. */
 /* dL -> z lookup built by check_vs_priors, nmma/em/model.py:249-267 (50 points). */
 int nmma_b200_set_redshift_table(nmma_b200_t* h, int n, const double* dist_grid, const double* z_grid);
 
@@ -162,7 +165,8 @@ int nmma_b200_set_constraints(nmma_b200_t* h, int n, const nmma_b200_param_src* 
  * uncorrected), evaluated per point at nu0 (1+z); coef ignored.  law LINEAR: coef[F] =
  * A_f / E(B-V) (R_V x the curve at the observer-frame wavelength); nu0 ignored.  law NONE: both
  * may be NULL.  Call after nmma_b200_set_svd (which resets it). */
-int nmma_b200_set_extinction(nmma_b200_t* h, int law, nmma_b200_param_src ebv, const double* nu0 /* F */,
+int nmma_b200_set_extinction(nmma_b200_t* h, int law, const nmma_b200_param_src* ebv /* NULL: const 0 */,
+                             const double* nu0 /* F */,
                              const double* coef /* F */);
 
 /* ---- compute ----------------------------------------------------------- */

@@ -56,12 +56,12 @@ SIGNATURES = {
     "nmma_b200_set_mlp": (C.c_int, [_h, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "nmma_b200_set_gp": (C.c_int, [_h, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "nmma_b200_set_sample_grid": (C.c_int, [_h, C.c_int, _dp]),
-    "nmma_b200_set_param_layout": (C.c_int, [_h, C.c_int, _sp, ParamSrc, ParamSrc, ParamSrc, C.c_int]),
+    "nmma_b200_set_param_layout": (C.c_int, [_h, C.c_int, _sp, _sp, _sp, _sp, C.c_int]),
     "nmma_b200_set_redshift_table": (C.c_int, [_h, C.c_int, _dp, _dp]),
     "nmma_b200_set_observations": (C.c_int, [_h, C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _dp]),
     "nmma_b200_set_systematics": (C.c_int, [_h, C.c_int, _ip, _dp, _ip, _ip, _sp, _dp]),
     "nmma_b200_set_constraints": (C.c_int, [_h, C.c_int, _sp, _dp, _dp]),
-    "nmma_b200_set_extinction": (C.c_int, [_h, C.c_int, ParamSrc, _dp, _dp]),
+    "nmma_b200_set_extinction": (C.c_int, [_h, C.c_int, _sp, _dp, _dp]),
     "nmma_b200_logl": (C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nmma_b200_logl_host": (C.c_int, [_h, _dp, C.c_int64, _dp]),
     "nmma_b200_logl_host_to_device": (C.c_int, [_h, _dp, C.c_int64, C.c_void_p]),

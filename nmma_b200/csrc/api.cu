@@ -541,8 +541,8 @@ int nmma_b200_set_sample_grid(nmma_b200_t* h, int S, const double* sample_times)
 }
 
 int nmma_b200_set_param_layout(nmma_b200_t* h, int P, const nmma_b200_param_src* model_params,
-                               nmma_b200_param_src luminosity_distance, nmma_b200_param_src timeshift,
-                               nmma_b200_param_src redshift, int z_mode) {
+                               const nmma_b200_param_src* luminosity_distance, const nmma_b200_param_src* timeshift,
+                               const nmma_b200_param_src* redshift, int z_mode) {
     if (!h) return NMMA_B200_ERR_ARG;
     if (!h->have_svd) return fail(h, NMMA_B200_ERR_STATE, "set_param_layout: call nmma_b200_set_svd first");
     if (P < 1 || !model_params) return fail(h, NMMA_B200_ERR_ARG, "set_param_layout: P < 1 or NULL model_params");
@@ -550,9 +550,9 @@ int nmma_b200_set_param_layout(nmma_b200_t* h, int P, const nmma_b200_param_src*
     h->P = P;
     h->xsrc.clear();
     for (int i = 0; i < h->d; ++i) h->xsrc.push_back(to_src(model_params[i]));
-    h->dl = to_src(luminosity_distance);
-    h->ts = to_src(timeshift);
-    h->zsrc = to_src(redshift);
+    h->dl = luminosity_distance ? to_src(*luminosity_distance) : ParamSrc{-1, 0, 1e-5};   // 10 pc, nmma/em/model.py:291-293
+    h->ts = timeshift ? to_src(*timeshift) : ParamSrc{-1, 0, 0.0};
+    h->zsrc = redshift ? to_src(*redshift) : ParamSrc{-1, 0, 0.0};
     h->zmode = z_mode;
     h->have_layout = true;
     h->dirty = true;
@@ -640,13 +640,13 @@ int nmma_b200_set_constraints(nmma_b200_t* h, int n, const nmma_b200_param_src* 
     return NMMA_B200_OK;
 }
 
-int nmma_b200_set_extinction(nmma_b200_t* h, int law, nmma_b200_param_src ebv, const double* nu0, const double* coef) {
+int nmma_b200_set_extinction(nmma_b200_t* h, int law, const nmma_b200_param_src* ebv, const double* nu0, const double* coef) {
     if (!h) return NMMA_B200_ERR_ARG;
     if (!h->have_svd) return fail(h, NMMA_B200_ERR_STATE, "set_extinction: call nmma_b200_set_svd first");
     if (law < NMMA_B200_EXT_NONE || law > NMMA_B200_EXT_LINEAR) return fail(h, NMMA_B200_ERR_ARG, "set_extinction: unknown law %d", law);
     const int F = h->F;
     h->ext_law = law;
-    h->ebv = to_src(ebv);
+    h->ebv = ebv ? to_src(*ebv) : ParamSrc{-1, 0, 0.0};
     h->ext_nu.assign(F, 0.0);
     h->ext_coef.assign(F, 0.0);
     if (law == NMMA_B200_EXT_P92_SMC_HOST) {

@@ -114,6 +114,7 @@ __device__ __forceinline__ PointScal point_setup(const DevCfg& cfg, const double
     ps.zc = -2.5 * log10(ps.z1);
     ps.bad = !(isfinite(ps.z1) && isfinite(ps.ts));
     ps.ebv = 0.0;
+#ifndef TCV_NO_EXT_CON   // timing experiment: round-1 point_setup (no extinction, no constraints)
     if (cfg.ext_law != 0) {
         ps.ebv = eval_src(cfg.ebv, row);
         ps.bad = ps.bad || !isfinite(ps.ebv);   // NaN magnitudes in every filter -> sanity_check fails
@@ -123,6 +124,7 @@ __device__ __forceinline__ PointScal point_setup(const DevCfg& cfg, const double
         const double v = eval_src(cfg.con_src[i], row);
         ps.bad = ps.bad || !(v > cfg.con_lo[i] && v < cfg.con_hi[i]);
     }
+#endif
     point_fast_fields(cfg, ps);
     return ps;
 }

@@ -315,16 +315,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a phase bug must not hang the sampler process (the C ABI promises a status, not a hang).  Every
-// 2^14 failed polls the global timer is read; a single wait that lasts longer than kMbarTimeoutNs traps, the launch
-// ends with cudaErrorLaunchFailure and the API call returns NMMA_B200_ERR_CUDA.  Normal waits last microseconds.
+// Waits must not hang the sampler process on a phase bug (the C ABI promises a status, not a hang).  Two forms:
+//   mbar_wait       bounded in place: every 2^14 failed polls the global timer is read and a wait longer than
+//                   kMbarTimeoutNs traps (the launch ends with cudaErrorLaunchFailure -> NMMA_B200_ERR_CUDA).  Used where
+//                   waits are rare (FFMA kernel, probes).
+//   mbar_wait_spin  plain spin for the tensor-core kernel, whose warps wait on every hand-off: the in-place bound cost 15 %
+//                   there (profiles/r02_variants.txt), so that kernel's otherwise idle TMEM-owner warp is the watchdog
+//                   instead (tc_kernel.cuh: it traps when no back-end warp has made progress for kMbarTimeoutNs).
 constexpr unsigned long long kMbarTimeoutNs = 8000000000ull;
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef TCV_MBAR_UNBOUNDED   // timing experiment (tools/build_variants.py)
+    while (!mbar_try_wait(bar, parity)) {}
+    return;
+#endif
     uint32_t polls = 0;
     unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {

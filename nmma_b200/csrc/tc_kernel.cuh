@@ -201,6 +201,8 @@ struct TcBars {
     uint64_t a2_full[kTcTiles][2], a2_free[kTcTiles][2];
     uint64_t c_full[kTcTiles][2], c_free[kTcTiles][2];
     uint32_t tmem_base;
+    uint32_t progress;   // bumped by the back-end warps once per (tile, filter): the watchdog's sign of life
+    uint32_t finished;   // role warps that have left their loops
 };
 
 template <int K, bool FAST, bool SPLIT>
@@ -247,6 +249,8 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 mbar_init(&bars->c_free[t][b], 4);
             }
         }
+        bars->progress = 0;
+        bars->finished = 0;
         mbar_fence_init();
     }
     if (warp == 11) tmem_alloc(&bars->tmem_base, 512);
@@ -304,7 +308,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     const int b = c & 1;
                     const uint32_t u = ubase + ((uint32_t)c >> 1);
                     uint32_t v[kTcChunk];
-                    mbar_wait(&bars->d1_full[t][b], u & 1);
+                    mbar_wait_spin(&bars->d1_full[t][b], u & 1);
                     tc_fence_after();
                     tmem_ld32(tbase + kColD1 + kTcChunk * b, v);
                     tmem_ld32(tbase + kColD1 + kTcChunk * b + 32, v + 32);
@@ -312,7 +316,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     if (c >= 2) {
                         // L2 of chunk c-2 done: its h_lo buffer is free (D1[b] was already rewritten by layer 1 of this
                         // chunk, queued behind it); if it closed a group, the partial is complete
-                        mbar_wait(&bars->a2_free[t][b], (u - 1) & 1);
+                        mbar_wait_spin(&bars->a2_free[t][b], (u - 1) & 1);
                         tc_fence_after();
                         if (((c - 2) & (kTcGroup - 1)) == kTcGroup - 1) {
                             uint32_t part[16];
@@ -353,7 +357,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 }
                 // drain: the last group's partial and the cross terms (NCH is a multiple of the group size)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) mbar_wait(&bars->a2_free[t][b], (ubase + half - 1) & 1);
+                for (int b = 0; b < 2; ++b) mbar_wait_spin(&bars->a2_free[t][b], (ubase + half - 1) & 1);
                 tc_fence_after();
                 {
                     uint32_t part[16], cr[16];
@@ -366,7 +370,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 tc_fence_before();
                 // ---- hand the coefficients (+ b2 in fp32, Keras Dense) to the back-end warps ----
                 const int slot = (int)(vseq & 1);
-                mbar_wait(&bars->c_free[t][slot], ((vseq >> 1) & 1) ^ 1);
+                mbar_wait_spin(&bars->c_free[t][slot], ((vseq >> 1) & 1) ^ 1);
                 float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
 #pragma unroll
                 for (int k = 0; k < K; ++k) cb[k * kTcTile] = okx ? acc[k] + cfg.b2[f * K + k] : CUDART_NAN_F;
@@ -407,10 +411,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 total_v += TC_PART_F1(blockIdx.x + it * gridDim.x) - TC_PART_F0(blockIdx.x + it * gridDim.x);
         }
         for (long long vv = 0; vv < total_v; ++vv, ++vseq) {
-            mbar_wait(&bars->a1_full[t], vseq & 1);
+            mbar_wait_spin(&bars->a1_full[t], vseq & 1);
 #pragma unroll
             for (int b = 0; b < 2; ++b) {  // prologue: layer 1 of chunks 0 and 1
-                mbar_wait(&bars->w_full[s1], p1);
+                mbar_wait_spin(&bars->w_full[s1], p1);
                 tc_fence_after();
                 if (elect_one()) l1(b);
                 __syncwarp();
@@ -421,8 +425,8 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     const bool more = c + b + 2 < NCH;
-                    if (more) mbar_wait(&bars->w_full[s1], p1);
-                    mbar_wait(&bars->a2_full[t][b], (ubase + ((uint32_t)c >> 1)) & 1);
+                    if (more) mbar_wait_spin(&bars->w_full[s1], p1);
+                    mbar_wait_spin(&bars->a2_full[t][b], (ubase + ((uint32_t)c >> 1)) & 1);
                     tc_fence_after();
                     if (elect_one()) {
                         const int cc = c + b;
@@ -466,7 +470,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         int f = TC_PART_F0(item), f1 = TC_PART_F1(item);
         for (long long vv = 0; vv < total_v; ++vv, ++vseq) {
             const int slot = (int)(vseq & 1);
-            mbar_wait(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
+            mbar_wait_spin(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&bars->b_full[slot], bbytes);
                 bulk_g2s(s_basis0 + slot * bslot, basis_src<FAST>(cfg, f, K), bbytes, &bars->b_full[slot]);
@@ -474,7 +478,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             __syncwarp();
             const float* src = cfg.tcpack + (size_t)f * NCH * kTcChunkFloats;
             for (int c = 0; c < NCH; ++c) {
-                mbar_wait(&bars->w_free[st], ph ^ 1);
+                mbar_wait_spin(&bars->w_free[st], ph ^ 1);
                 if (elect_one()) {
 #ifdef TCV_NO_WLOAD
                     mbar_arrive(&bars->w_full[st]);
@@ -510,7 +514,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             for (int f = TC_PART_F0(item), f1 = TC_PART_F1(item); f < f1; ++f, ++vseq) {
                 const int slot = (int)(vseq & 1);
                 const uint32_t par = (vseq >> 1) & 1;
-                mbar_wait(&bars->c_full[t][slot], par);
+                mbar_wait_spin(&bars->c_full[t][slot], par);
                 const float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
                 float cf[K];
 #pragma unroll
@@ -520,7 +524,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->c_free[t][slot]);
-                mbar_wait(&bars->b_full[slot], par);
+                mbar_wait_spin(&bars->b_full[slot], par);
                 if (ok) {
                     const double* basis = reinterpret_cast<const double*>(s_basis0 + slot * bslot);
 #ifdef TCV_NO_BACKEND
@@ -538,13 +542,34 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->b_free[slot]);
+                if (lane == 0) {
+                    mbar_arrive(&bars->b_free[slot]);
+                    atomicAdd(&bars->progress, 1u);
+                }
             }
             if (live) {
                 const bool good = ok && isfinite(logl);
                 if (fsplit == 1) out[n] = good ? logl : NMMA_SENTINEL;
                 else out[n * fsplit + item % fsplit] = good ? logl : CUDART_NAN;
             }
+        }
+    }
+    if (warp != 11) {
+        __syncwarp();
+        if (lane == 0) atomicAdd(&bars->finished, 1u);
+    } else if (lane == 0) {
+        // watchdog (the TMEM-owner warp has nothing else to do): the hand-off waits above spin without a bound, so a
+        // phase bug would hang the sampler process; no progress of any back-end warp for kMbarTimeoutNs -> trap
+        volatile uint32_t* fin = &bars->finished;
+        volatile uint32_t* prog = &bars->progress;
+        uint32_t last = *prog;
+        unsigned long long t_last = global_timer_ns();
+        while (*fin < (uint32_t)(kTcThreads / 32 - 1)) {
+            __nanosleep(20000);
+            const uint32_t p = *prog;
+            const unsigned long long now = global_timer_ns();
+            if (p != last) { last = p; t_last = now; }
+            else if (now - t_last > kMbarTimeoutNs) __trap();
         }
     }
     tc_fence_before();

@@ -105,10 +105,9 @@ class KilonovaEngine:
     def set_param_layout(self, P: int, model_params: Sequence[ParamSrc], luminosity_distance: ParamSrc = None,
                          timeshift: ParamSrc = None, redshift: ParamSrc = None, z_mode: int = L.Z_ZERO):
         arr = (ParamSrc * len(model_params))(*model_params)
-        dl = luminosity_distance if luminosity_distance is not None else ParamSrc.const(1e-5)
-        ts = timeshift if timeshift is not None else ParamSrc.const(0.0)
-        zs = redshift if redshift is not None else ParamSrc.const(0.0)
-        self._check(self._lib.nmma_b200_set_param_layout(self._h, int(P), arr, dl, ts, zs, int(z_mode)))
+        ref = lambda s: C.byref(s) if s is not None else None      # NULL -> the reference's default (10 pc, 0, 0)
+        self._check(self._lib.nmma_b200_set_param_layout(self._h, int(P), arr, ref(luminosity_distance), ref(timeshift),
+                                                         ref(redshift), int(z_mode)))
         self.P = int(P)
 
     def set_redshift_table(self, dist_grid, z_grid):
@@ -162,12 +161,12 @@ class KilonovaEngine:
 
     def set_extinction(self, law: int, ebv: ParamSrc = None, nu0=None, coef=None):
         """Extinction law (``nmma/em/model.py:323-350``): ``nu0[F]`` [Hz] for P92_SMC_host, ``coef[F]`` for the linear law."""
-        ebv = ebv if ebv is not None else ParamSrc.const(0.0)
         nu = _f64(nu0) if nu0 is not None else None
         cf = _f64(coef) if coef is not None else None
         for a in (nu, cf):
             assert a is None or a.shape == (self.F,)
-        self._check(self._lib.nmma_b200_set_extinction(self._h, int(law), ebv, _dptr(nu) if nu is not None else None,
+        self._check(self._lib.nmma_b200_set_extinction(self._h, int(law), C.byref(ebv) if ebv is not None else None,
+                                                       _dptr(nu) if nu is not None else None,
                                                        _dptr(cf) if cf is not None else None))
 
     # ---- compute ----------------------------------------------------------------------

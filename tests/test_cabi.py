@@ -84,3 +84,18 @@ def test_sass_tensor_core_kernel_is_tcgen05():
     assert counts["UTCHMMA"] >= 20 and counts["LDTM"] >= 4 and counts["STTM"] >= 8, counts
     assert counts["UTCBAR"] >= 4 and counts["UBLKCP"] >= 2 and counts["SYNCS"] >= 20, counts
     assert not re.search(r"\bHMMA|\bHGMMA|\bIMMA", body)
+
+
+def test_no_struct_passed_by_value():
+    """Plain pointers and sizes only.  A {int32, int32, double} struct by value travels in one integer and one SSE register;
+    ctypes (CPython 3.12 / libffi) gives every such argument of a call the LAST one's double, so a ctypes binder of a
+    by-value prototype silently evaluated at luminosity_distance = the redshift constant (found by the
+    OpticalLightCurve dict test of round 2).  The header therefore takes nmma_b200_param_src by pointer everywhere."""
+    text = open(os.path.join(ROOT, "include", "nmma_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for proto in re.findall(r"\bnmma_b200_[a-z_0-9]+\s*\(([^;{]*)\)\s*;", text):
+        for arg in proto.split(","):
+            assert not re.search(r"\bnmma_b200_param_src\s+\w+\s*$", arg.strip()), f"by-value struct argument: {arg.strip()}"
+    from nmma_b200 import _lib
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert not any(isinstance(a, type) and issubclass(a, ctypes.Structure) for a in argtypes), name

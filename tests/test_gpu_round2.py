@@ -111,9 +111,19 @@ def test_optical_light_curve_dict_entry(torch_cuda):
     want = harness.oracle_logl(olik, fixed, np.array([[p_fixed[c] for c in cols]]), cols)[0]
     assert lik2.log_likelihood(p_fixed) == pytest.approx(want, rel=1e-4)
     # without priors every numeric key of the first call becomes a column
-    lik3 = OpticalLightCurve(model, filters, legacy, trig, error_budget=1.0)
-    with pytest.raises(ValueError):                                                    # luminosity_distance without prior / table
+    model3 = SVDLightCurveModel("Bu2019lm", svd_mag_model=core, interpolation_type="tensorflow", filters=filters)
+    lik3 = OpticalLightCurve(model3, filters, legacy, trig, error_budget=1.0)
+    with pytest.raises(ValueError):          # luminosity_distance without a prior: the reference's per-call z_at_value path
         lik3.log_likelihood(dict(zip(cols, pts[0])))
+    p3 = dict(zip(cols, pts[2]))
+    z3 = float(np.interp(p3.pop("luminosity_distance"), *model._z_table))
+    lik4 = OpticalLightCurve(SVDLightCurveModel("Bu2019lm", svd_mag_model=core, interpolation_type="tensorflow", filters=filters),
+                             filters, legacy, trig, error_budget=1.0)
+    p3["redshift"] = z3                      # dict with an explicit redshift and the default distance (1e-5 Mpc = 10 pc)
+    want3 = harness.oracle_logl(harness.build_oracle_likelihood(core, model.model_parameters, filters,
+                                                                np.asarray(model.model_times, float), filters, lc_data, {})[0],
+                                {}, np.array([list(p3.values())]), list(p3.keys()))[0]
+    assert lik4.log_likelihood(p3) == pytest.approx(want3, rel=1e-4)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -5,8 +5,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, bench
 path = int(sys.argv[1]); M = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000; reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-wl = bench.build_workload(); cols = list(wl["priors"].keys())
-lik, model, handler = bench.gpu_likelihood(wl, 0)
+cfg = os.environ.get("TC_TIME_CONFIG", "c2")
+wl = bench.make_spec(cfg); cols = wl["cols"]
+lik = bench.gpu_likelihood(wl, 0)
 eng = lik.sub_model.engine_for(cols); eng.set_option("path", path)
 big, _ = wl["priors"].sample_array(M, np.random.default_rng(6), cols)
 bigd = torch.from_numpy(big).cuda(); out = torch.empty(M, dtype=torch.float64, device="cuda")
