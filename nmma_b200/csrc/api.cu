@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "handle.h"
+#include "gp_kernel.cuh"  // shared-memory footprint of the fused GP kernel
 #include "tc_kernel.cuh"  // layout constants of the tensor-core kernel (its weight pack is built here)
 
 using namespace nmma;
@@ -293,6 +294,11 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         }
         if (int rc = upload(h, h->gpX, &c.gpX)) return rc;
         if (int rc = upload(h, A, &c.gpA)) return rc;
+        std::vector<double> AT(n * h->Ntr);
+        for (int f = 0; f < F; ++f)
+            for (int k = 0; k < K; ++k)
+                for (int t = 0; t < h->Ntr; ++t) AT[((size_t)f * h->Ntr + t) * K + k] = A[((size_t)f * K + k) * h->Ntr + t];
+        if (int rc = upload(h, AT, &c.gpAT)) return rc;
         if (int rc = upload(h, q, &c.gp_q)) return rc;
         if (int rc = upload(h, h->gpRa, &c.gp_ra)) return rc;
         if (int rc = upload(h, h->gpYm, &c.gp_ym)) return rc;
@@ -403,6 +409,12 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                              fused_smem_bytes(d, K, T, c.S, nobs) <= 227 * 1024;
         h->tc_supported = (h->kind == 0) && direct && K == 10 && c.tc_nch > 0 &&
                           tc_smem_bytes(K, T, c.S, nobs) <= 227 * 1024;
+        // fused GP kernel: gf_pow takes rint(256 a log2(base)) from the low word of a double, i.e. needs it below 2^31:
+        // a <= 1e5 (the sklearn bound of RationalQuadratic.alpha) leaves room for base < 2^80
+        bool gp_alpha_ok = true;
+        for (double a : h->gpRa) gp_alpha_ok = gp_alpha_ok && a > 0.0 && a <= 1e5;
+        h->gp_fused_supported = (h->kind == 1) && direct && gp_fused_has(d, K) && gp_alpha_ok &&
+                                gf_smem_bytes(h->Ntr, d) <= 227 * 1024;
     }
     h->dirty = false;
     return NMMA_B200_OK;
@@ -450,6 +462,8 @@ int nmma_b200_destroy(nmma_b200_t* h) {
     free_dev(h);
     if (h->coeff_scratch) cudaFree(h->coeff_scratch);
     if (h->tc_parts) cudaFree(h->tc_parts);
+    if (h->gp_parts) cudaFree(h->gp_parts);
+    if (h->gp_tickets) cudaFree(h->gp_tickets);
     if (h->pr_dev) cudaFree(h->pr_dev);
     if (h->pr_tab_dev) cudaFree(h->pr_tab_dev);
     if (h->sweep_scratch) cudaFree(h->sweep_scratch);
@@ -679,13 +693,17 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused kernel unavailable for this configuration (GP path, averaged filters, or d/K not instantiated)");
     if (path == 3 && !h->tc_supported)
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "tensor-core kernel unavailable for this configuration (GP path, averaged filters, d > 7 or n_coeff != 10)");
+    if (path == 4 && !h->gp_fused_supported)
+        return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused GP kernel unavailable for this configuration (MLP path, averaged filters, d outside 2..7, n_coeff != 10 or alpha > 1e5)");
     if (path == 0) {
         if (h->tc_supported && N >= h->opt_tc_min) path = 3;
+        else if (h->gp_fused_supported && N >= h->opt_gp_min) path = 4;
         else path = (h->fused_supported && N >= h->opt_fused_min) ? 1 : 2;
     }
     h->last_path = path;
     if (path == 3) return launch_tc(h, points_dev, N, out_dev, st);
     if (path == 1) return launch_fused(h, points_dev, N, out_dev, st);
+    if (path == 4) return launch_gp(h, points_dev, N, out_dev, st);
     const size_t FK = (size_t)h->F * h->K;
     const long long chunk = std::min<long long>(N, kTwoStageChunk);
     if (int rc = ensure_scratch(h, (size_t)chunk * FK)) return rc;
@@ -859,9 +877,10 @@ int nmma_b200_mags(nmma_b200_t* h, const double* points_dev, int64_t N, int appa
 int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     if (!h || !key) return NMMA_B200_ERR_ARG;
     const std::string k(key);
-    if (k == "path") { if (value < 0 || value > 3) return fail(h, NMMA_B200_ERR_ARG, "path must be 0 (auto), 1 (fused FFMA), 2 (two-stage) or 3 (tensor core)"); h->opt_path = (int)value; }
+    if (k == "path") { if (value < 0 || value > 4) return fail(h, NMMA_B200_ERR_ARG, "path must be 0 (auto), 1 (fused FFMA), 2 (two-stage), 3 (tensor core) or 4 (fused GP)"); h->opt_path = (int)value; }
     else if (k == "fused_min_points") h->opt_fused_min = value;
     else if (k == "tc_min_points") h->opt_tc_min = value;
+    else if (k == "gp_min_points") h->opt_gp_min = value;
     else if (k == "max_ctas") h->opt_max_ctas = (int)value;
     else if (k == "pipeline_blocks") { if (value < 1 || value > 64) return fail(h, NMMA_B200_ERR_ARG, "pipeline_blocks must be 1..64"); h->opt_pipeline = (int)value; }
     else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }
@@ -882,6 +901,7 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
     else if (k == "ctas_per_sm") *value = h->last_ctas_per_sm;
     else if (k == "fused_supported") { if (int rc = finalize(h, true)) return rc; *value = h->fused_supported ? 1 : 0; }
     else if (k == "tc_supported") { if (int rc = finalize(h, true)) return rc; *value = h->tc_supported ? 1 : 0; }
+    else if (k == "gp_fused_supported") { if (int rc = finalize(h, true)) return rc; *value = h->gp_fused_supported ? 1 : 0; }
     else if (k == "algorithmic_flop_per_eval") {
         // F * [2 H (d + K) + 2 T K] (MLP) or Ntr*3d + F*K*Ntr*8 + F*2*T*K (GP)
         if (h->kind == 0) *value = (int64_t)h->F * (2LL * h->H * (h->d + h->K) + 2LL * h->T * h->K);

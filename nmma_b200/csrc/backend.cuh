@@ -43,6 +43,7 @@ struct DevCfg {
     // GP front end
     const double* gpX;    // Ntr*d
     const double* gpA;    // F*K*Ntr  constant_value * alpha_
+    const double* gpAT;   // F*Ntr*K  the same, the K values of a training row adjacent (fused GP kernel)
     const double* gp_q;   // F*K      1 / (2 * alpha * length_scale^2)
     const double* gp_ra;  // F*K      alpha
     const double* gp_ym;  // F*K

@@ -1,0 +1,160 @@
+// Fused sklearn_gp path: GP mean -> SVD coefficients -> light curve -> log-likelihood in ONE launch, no coefficient scratch.
+//
+//   c_{f,k}(x) = ystd * sum_t C^2 alpha_t (1 + |x - X_t|^2 q)^(-a) + ymean ,   q = 1 / (2 a l^2)
+//   (sklearn RationalQuadratic.__call__ + GaussianProcessRegressor.predict, nmma/em/lightcurve_generation.py:200-211)
+//
+// F K Ntr = 29 610 kernel values per evaluation for Ka2017 (9 filters x 10 coefficients x 329 training rows), each an
+// fp64 pow (the alpha-weighted sum cancels up to 3e5 : 1, so the values need ~1e-13 relative accuracy): the path is bound
+// by the fp64 pipe (DFMA issues every 2 cycles per SM sub-partition, profiles/r01_fp64_rate.txt).  The two-stage
+// coeff_gp_kernel reached 47 % of that pipe (profiles/r02_gp_backend_before_summary.json): 24 fp64 + 49 other
+// instructions per value, three int<->fp64 conversions on the XU pipe, three random 8-byte shared-memory gathers with
+// ~5-way bank conflicts (70 % of the shared-memory wavefront peak).  This kernel:
+//   * thread = point, warp = work item (32-point tile, model filter), one persistent 16-warp CTA per SM; the K coefficient
+//     sums of the filter are K independent dependency chains per thread (ILP instead of occupancy); all per-pair
+//     constants and the alpha values are warp-uniform; r^2 is computed once per training row and reused by the K pairs;
+//   * gf_pow: 17 fp64 instructions per value.  log2: base = 2^e m, u = m r_i - 1 with r_i an fp32 reciprocal of the
+//     centre of the i-th of 256 mantissa cells (|u| <= 2^-9; the fma is exact), log2 m = -log2 r_i + u P3(u) with an
+//     interpolated (near-minimax) cubic, error 1.1e-15 absolute.  exp2: t = -256 a log2(base); k = rint(t) and the
+//     remainder by the 1.5 * 2^52 trick (no F2I / I2F), 2^(k/256) = 2^(k >> 8) * table[k & 255] * (1 + xr E3(xr)), error
+//     5e-18.  One conversion (the exponent e) is left on the XU pipe.
+//   * the two tables are replicated per bank group (8 x 16-byte log entries per quarter warp, 16 x 8-byte exp entries per
+//     half warp): every gather is conflict-free, 4 + 2 wavefronts per warp-level value instead of ~15;
+//   * the coefficients never leave registers: each warp scores its filter's observations right away through the same
+//     fused_filter_logl back end as the MLP kernels (basis rows read through L1); the per-filter sums of a tile (8 B per
+//     point and filter) are added in filter order by the warp that finishes the tile's last filter.
+// Restated operation by operation in tests/test_rq_pow.py (accuracy vs a 40-digit reference).
+#pragma once
+#include "kernels.cuh"
+
+namespace nmma {
+
+constexpr int kGfTab = 256;
+constexpr int kGfWarps = 16;                   // one CTA per SM: 4 warps per sub-partition at <= 128 registers
+constexpr int kGfLogBytes = kGfTab * 8 * 16;   // {r_i, -log2 r_i} x 8 replicas
+constexpr int kGfExpBytes = kGfTab * 16 * 8;   // 2^(j/256) x 16 replicas
+
+inline size_t gf_smem_bytes(int Ntr, int d) {
+    return (size_t)kGfLogBytes + kGfExpBytes + ((size_t)Ntr * d * sizeof(double) + 127) / 128 * 128;
+}
+
+// (1 + r2 q)^(-a) with na = -256 a.  `ltab` / `etab` already carry this lane's replica offset.
+// Valid for 256 a log2(base) < 2^31 (a <= 1e5, the sklearn bound, and base < 2^80; checked / documented in launch_gp.cu).
+__device__ __forceinline__ double gf_pow(double r2, double q, double na, const unsigned char* __restrict__ ltab,
+                                         const unsigned char* __restrict__ etab) {
+    const double base = fma(r2, q, 1.0);
+    const int hi = __double2hiint(base);
+    const double2 ent = *reinterpret_cast<const double2*>(ltab + ((hi >> 5) & 0x7f80));   // cell (hi >> 12) & 255, 128 B apart
+    // u = m r_i - 1 with m = base 2^-e: the exponent is taken off r_i instead (one integer add on its high word)
+    const double rs = __hiloint2double(__double2hiint(ent.x) + 0x3ff00000 - (hi & 0x7ff00000), __double2loint(ent.x));
+    const double ed = (double)((hi >> 20) - 1023);
+    const double u = fma(base, rs, -1.0);
+    double p = fma(-0.36067471452205946, u, 0.4808994921226281);
+    p = fma(p, u, -0.7213475204440083);
+    p = fma(p, u, 1.4426950408883954);
+    const double lg2 = fma(p, u, ent.y) + ed;
+    const double t = na * lg2;
+    const double s = t + 6755399441055744.0;          // 1.5 * 2^52: the low word of s is rint(t)
+    const double xr = t - (s - 6755399441055744.0);   // |xr| <= 1/2
+    const int k = max(__double2loint(s), -1020 * 256);   // underflow: the value becomes ~2^-1020 instead of a wrapped exponent
+    double g = fma(2.2393953277407236e-12, xr, 3.308302983832675e-9);
+    g = fma(g, xr, 3.665565596910102e-6);
+    g = fma(g, xr, 0.0027076061740622769);
+    const double e2 = *reinterpret_cast<const double*>(etab + ((k << 7) & 0x7f80));        // 2^((k & 255) / 256)
+    const double v = fma(e2, g * xr, e2);             // in [0.99, 2.01)
+    return __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));      // * 2^(k >> 8)
+}
+
+// Work item = (32-point tile, model filter); a warp owns an item, the thread a point.  The per-filter sums of a tile go
+// through `parts` [tile][F][32]; the warp that finishes a tile's last filter (global ticket `tickets[tile]`, which it
+// resets for the next launch) adds them in filter order, so the result does not depend on the schedule.
+// FAST = sample grid is the (uniform) training grid itself (fp32 back end), else the generic fp64 back end.
+template <int D, int K, bool FAST>
+__global__ void __launch_bounds__(kGfWarps * 32, 1)
+fused_gp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ out,
+                     double* __restrict__ parts, unsigned int* __restrict__ tickets) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Ntr = cfg.Ntr, F = cfg.F;
+    double* Xs = reinterpret_cast<double*>(smem + kGfLogBytes + kGfExpBytes);
+    for (int i = tid; i < kGfTab; i += blockDim.x) {
+        const float cf = 1.0f + ((float)i + 0.5f) / (float)kGfTab;   // centre of mantissa cell i, exact in fp32
+        const double r = (double)(1.0f / cf);                          // the table holds the log of exactly this value
+        const double2 ent = make_double2(r, -log2(r));
+        double2* le = reinterpret_cast<double2*>(smem) + i * 8;
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) le[rep] = ent;
+        const double e = exp2((double)i / kGfTab);
+        double* ee = reinterpret_cast<double*>(smem + kGfLogBytes) + i * 16;
+#pragma unroll
+        for (int rep = 0; rep < 16; ++rep) ee[rep] = e;
+    }
+    for (int i = tid; i < Ntr * D; i += blockDim.x) Xs[i] = cfg.gpX[i];
+    __syncthreads();
+    const unsigned char* ltab = smem + (lane & 7) * 16;
+    const unsigned char* etab = smem + kGfLogBytes + (lane & 15) * 8;
+
+    const long long ntiles = (N + 31) / 32;
+    const long long nitems = ntiles * F;
+    for (long long item = (long long)blockIdx.x * kGfWarps + warp; item < nitems; item += (long long)gridDim.x * kGfWarps) {
+        const long long tile = item / F;
+        const int f = (int)(item - tile * F);
+        const long long n = tile * 32 + lane;
+        const bool live = n < N;
+        const double* row = pts + (live ? n : N - 1) * cfg.P;
+        const PointScal ps = point_setup(cfg, row);
+        bool ok = !ps.bad && !cfg.static_fail;
+        // the scaled input depends on the filter only through param_mins/maxs, which training.py:216-230 shares across
+        // filters (checked on the host)
+        double x[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            x[i] = scaled_input(cfg, 0, i, row);
+            ok = ok && isfinite(x[i]);
+        }
+        double qk[K], nak[K], acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            qk[k] = cfg.gp_q[f * K + k];
+            nak[k] = -256.0 * cfg.gp_ra[f * K + k];
+            acc[k] = 0.0;
+        }
+        const double* __restrict__ a = cfg.gpAT + (size_t)f * Ntr * K;   // [Ntr][K]: the K alphas of a row are adjacent
+        const double* __restrict__ xt = Xs;
+#pragma unroll 1
+        for (int t = 0; t < Ntr; ++t, a += K, xt += D) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const double df = x[i] - xt[i];
+                r2 = fma(df, df, r2);
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = fma(gf_pow(r2, qk[k], nak[k], ltab, etab), __ldg(a + k), acc[k]);
+        }
+        double c[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            c[k] = cfg.gp_ys[f * K + k] * acc[k] + cfg.gp_ym[f * K + k];
+            ok = ok && isfinite(c[k]);
+        }
+        double lsum = CUDART_NAN;
+        if (ok) lsum = fused_filter_logl<K, FAST>(cfg, f, c, ps, row, basis_src<FAST>(cfg, f, K), cfg.o_pack, cfg.samp);
+        // ---- hand the filter's sum in; the last filter of the tile to arrive adds them up in filter order ----
+        double* tp = parts + (size_t)tile * F * 32;
+        __stcg(tp + f * 32 + lane, lsum);
+        __threadfence();
+        __syncwarp();
+        unsigned int old = 0;
+        if (lane == 0) old = atomicAdd(&tickets[tile], 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == (unsigned)(F - 1)) {
+            __threadfence();
+            double s = 0.0;
+            for (int j = 0; j < F; ++j) s += __ldcg(tp + j * 32 + lane);
+            if (live) out[n] = isfinite(s) ? s : NMMA_SENTINEL;
+            if (lane == 0) tickets[tile] = 0;   // ready for the next launch on this handle
+        }
+    }
+}
+
+}  // namespace nmma

@@ -64,6 +64,10 @@ struct nmma_b200_handle {
     double* coeff_scratch = nullptr;
     double* tc_parts = nullptr;       // per-part sums of a filter-split tensor-core launch (launch_tc.cu)
     size_t tc_parts_cap = 0;
+    double* gp_parts = nullptr;       // fused GP kernel: per-(tile, filter) sums and per-tile tickets (launch_gp.cu)
+    unsigned int* gp_tickets = nullptr;
+    size_t gp_parts_cap = 0, gp_tickets_cap = 0;
+    bool gp_fused_supported = false;
     size_t coeff_cap = 0;
     double* stage_in_dev = nullptr;
     double* stage_out_dev = nullptr;
@@ -80,6 +84,7 @@ struct nmma_b200_handle {
     long long opt_tc_min = 1;         // tensor-core path from the first point: with the filters of a super-tile split over CTAs
                                       // (launch_tc.cu) one call takes 39 us at N = 1 and 40-46 us up to 4096 points, the two-stage
                                       // kernels 47 us + 0.6 us per point (tools/latency_breakdown.py, tools/latency.py)
+    long long opt_gp_min = 2048;      // fused GP kernel (thread = point) from this batch size; below, the two-stage kernels (lanes = training rows)
     int opt_max_ctas = 0;
     int opt_no_fast = 0;
     int opt_zero_copy = 1;            // set_option "zero_copy": small host batches are read / written in place (pinned memory)
@@ -98,6 +103,8 @@ int fail(nmma_b200_t* h, int code, const char* fmt, ...);
 int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
 bool fused_has(int d, int K);
 int launch_tc(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
+int launch_gp(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
+bool gp_fused_has(int d, int K);
 }  // namespace nmma
 
 #define CU(call)                                                                          \

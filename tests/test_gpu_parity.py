@@ -47,6 +47,12 @@ def _paths(lik, pts, cols):
         eng.set_option("no_fast_backend", 1)
         out["fused_tc_generic"] = eng.logl_host(pts)
         eng.set_option("no_fast_backend", 0)
+    if eng.get_info("gp_fused_supported"):
+        eng.set_option("path", 4)                             # fused GP kernel (thread = point, item = (tile, filter))
+        out["fused_gp"] = eng.logl_host(pts)
+        eng.set_option("no_fast_backend", 1)
+        out["fused_gp_generic"] = eng.logl_host(pts)
+        eng.set_option("no_fast_backend", 0)
     eng.set_option("path", 0)
     return out
 
@@ -251,6 +257,25 @@ def test_ka2017_gp(torch_cuda):
     ref = harness.oracle_logl(olik, fixed, pts, cols)
     got = lik.log_likelihood_batch(pts, cols)
     print("ka2017 gp", assert_logl_close(got, ref), "sentinels", int((ref == SENTINEL).sum()))
+    for name, got_p in _paths(lik, pts, cols).items():
+        print("ka2017 gp", name, assert_logl_close(got_p, ref))
+    # fused GP kernel (gf_pow, per-tile tickets) against the two-stage kernels (rq_pow) on a batch with a ragged last tile:
+    # with the generic fp64 back end both evaluate the same formulas, so they agree far below the tolerance
+    eng = lik.sub_model.engine_for(cols)
+    assert eng.get_info("gp_fused_supported") == 1
+    big, _ = priors.sample_array(32 * 150 + 7, np.random.default_rng(22), cols)
+    big[5, cols.index("log10_mej")] = np.nan
+    eng.set_option("path", 2); two = eng.logl_host(big)
+    eng.set_option("path", 4); eng.set_option("no_fast_backend", 1); gen = eng.logl_host(big)
+    eng.set_option("no_fast_backend", 0); fast = eng.logl_host(big); again = eng.logl_host(big)
+    eng.set_option("path", 0); auto = eng.logl_host(big)
+    assert eng.get_info("last_path") == 4                     # the automatic path of a large GP batch
+    sent = two == SENTINEL
+    assert sent[5] and np.array_equal(sent, gen == SENTINEL) and np.array_equal(sent, fast == SENTINEL)
+    ok = ~sent
+    assert np.abs(gen[ok] - two[ok]).max() / np.maximum(1.0, np.abs(two[ok])).max() < 1e-9
+    assert_logl_close(fast, two)
+    assert np.array_equal(fast, again) and np.array_equal(fast, auto)   # schedule-independent sums, tickets reset
     # GP coefficients against sklearn.predict to 1e-9 relative (cancellation ~1e5 in k.alpha)
     eng = lik.sub_model.engine_for(cols)
     c_gpu = eng.coeffs(pts[:8]).cpu().numpy()
