@@ -486,7 +486,7 @@ def gpu_arm(args):
             out.update({"bound": "fp64 (CUDA cores: F K Ntr kernel values (1 + r^2 q)^-alpha per evaluation)",
                         "achieved": achieved, "peak": pk["dfma"], "unit": "TFLOP/s", "frac": achieved / pk["dfma"],
                         "peak_source": "fp64 FMA micro-benchmark measured in this run (nmma_b200_dfma_peak)",
-                        "kernel": "gp_logl_kernel" if eng.get_info("last_path") == 4 else "coeff_gp_kernel + backend_logl_kernel"})
+                        "kernel": "fused_gp_logl_kernel" if eng.get_info("last_path") == 4 else "coeff_gp_kernel + backend_logl_kernel"})
         elif path == 3:
             executed = eng.get_info("tc_executed_flop_per_eval")
             out.update({"bound": "tensor", "achieved": achieved, "peak": pk["tf32"], "unit": "TFLOP/s",

@@ -22,7 +22,14 @@
 //   * the coefficients never leave registers: each warp scores its filter's observations right away through the same
 //     fused_filter_logl back end as the MLP kernels (basis rows read through L1); the per-filter sums of a tile (8 B per
 //     point and filter) are added in filter order by the warp that finishes the tile's last filter.
-// Restated operation by operation in tests/test_rq_pow.py (accuracy vs a 40-digit reference).
+// Measured (profiles/r02_gp_fused_*): 10.5 -> 22 M evals/s on config 4; fp64 pipe 59 %.  What bounds it now is not the pipe
+// but operand delivery and issue slots: a DFMA with three distinct register operands issues every 3 cycles, not 2
+// (tools/fp64_rate.cu: "DFMA3r"), and the ~20 integer / load instructions per value cost almost a full slot each next to
+// the fp64 stream; 8, 12, 16 or 20 warps per SM and 2- or 10-way interleaving all land within 5 % of each other.  The
+// per-pair constants cannot be moved off the register file: ptxas loads constant-bank / kernel-parameter operands into
+// vector registers inside the loop (tried: parameter struct indexed by a uniform filter index, and 16 loop instances
+// with compile-time offsets: 20.9 and 19.3 M evals/s).
+// gf_pow is restated operation by operation in tests/test_rq_pow.py (accuracy vs a 40-digit reference).
 #pragma once
 #include "kernels.cuh"
 
@@ -62,6 +69,56 @@ __device__ __forceinline__ double gf_pow(double r2, double q, double na, const u
     const double e2 = *reinterpret_cast<const double*>(etab + ((k << 7) & 0x7f80));        // 2^((k & 255) / 256)
     const double v = fma(e2, g * xr, e2);             // in [0.99, 2.01)
     return __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));      // * 2^(k >> 8)
+}
+
+// The same arithmetic for the K pairs of one training row, written stage by stage so that the K dependency chains are in
+// flight together (a dependent DFMA waits ~8 cycles, tools/fp64_rate.cu "DFMA chain1").
+template <int K>
+__device__ __forceinline__ void gf_pow_row(double r2, const double (&qk)[K], const double (&nak)[K],
+                                           const double* __restrict__ a, double (&acc)[K],
+                                           const unsigned char* __restrict__ ltab, const unsigned char* __restrict__ etab) {
+    double base[K], u[K], l2[K], ed[K], p[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) base[k] = fma(r2, qk[k], 1.0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int hi = __double2hiint(base[k]);
+        const double2 ent = *reinterpret_cast<const double2*>(ltab + ((hi >> 5) & 0x7f80));
+        const double rs = __hiloint2double(__double2hiint(ent.x) + 0x3ff00000 - (hi & 0x7ff00000), __double2loint(ent.x));
+        ed[k] = (double)((hi >> 20) - 1023);
+        l2[k] = ent.y;
+        u[k] = fma(base[k], rs, -1.0);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = fma(-0.36067471452205946, u[k], 0.4808994921226281);
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = fma(p[k], u[k], -0.7213475204440083);
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = fma(p[k], u[k], 1.4426950408883954);
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = fma(p[k], u[k], l2[k]) + ed[k];     // log2(base)
+    double s[K], xr[K], g[K];
+    int kk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) s[k] = fma(nak[k], p[k], 6755399441055744.0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        xr[k] = fma(nak[k], p[k], -(s[k] - 6755399441055744.0));
+        kk[k] = max(__double2loint(s[k]), -1020 * 256);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) g[k] = fma(2.2393953277407236e-12, xr[k], 3.308302983832675e-9);
+#pragma unroll
+    for (int k = 0; k < K; ++k) g[k] = fma(g[k], xr[k], 3.665565596910102e-6);
+#pragma unroll
+    for (int k = 0; k < K; ++k) g[k] = fma(g[k], xr[k], 0.0027076061740622769) * xr[k];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double e2 = *reinterpret_cast<const double*>(etab + ((kk[k] << 7) & 0x7f80));
+        const double v = fma(e2, g[k], e2);
+        const double vs = __hiloint2double(__double2hiint(v) + ((kk[k] >> 8) << 20), __double2loint(v));
+        acc[k] = fma(vs, __ldg(a + k), acc[k]);
+    }
 }
 
 // Work item = (32-point tile, model filter); a warp owns an item, the thread a point.  The per-filter sums of a tile go
@@ -128,8 +185,7 @@ fused_gp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 const double df = x[i] - xt[i];
                 r2 = fma(df, df, r2);
             }
-#pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = fma(gf_pow(r2, qk[k], nak[k], ltab, etab), __ldg(a + k), acc[k]);
+            gf_pow_row<K>(r2, qk, nak, a, acc, ltab, etab);
         }
         double c[K];
 #pragma unroll

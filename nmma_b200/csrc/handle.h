@@ -84,7 +84,7 @@ struct nmma_b200_handle {
     long long opt_tc_min = 1;         // tensor-core path from the first point: with the filters of a super-tile split over CTAs
                                       // (launch_tc.cu) one call takes 39 us at N = 1 and 40-46 us up to 4096 points, the two-stage
                                       // kernels 47 us + 0.6 us per point (tools/latency_breakdown.py, tools/latency.py)
-    long long opt_gp_min = 2048;      // fused GP kernel (thread = point) from this batch size; below, the two-stage kernels (lanes = training rows)
+    long long opt_gp_min = 4096;      // fused GP kernel (thread = point) from this batch size; below, the two-stage kernels (lanes = training rows)
     int opt_max_ctas = 0;
     int opt_no_fast = 0;
     int opt_zero_copy = 1;            // set_option "zero_copy": small host batches are read / written in place (pinned memory)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Build timing-experiment variants of the tensor-core kernel: libnmma_b200.so relinked with launch_tc.cu compiled
-under -DTCV_* switches (tc_kernel.cuh).  python tools/build_variants.py NAME=FLAG[,FLAG...] ...
+"""Build timing-experiment variants of one translation unit: libnmma_b200.so relinked with that unit compiled under extra
+-D switches (TCV_* in tc_kernel.cuh, GPV_* in gp_kernel.cuh).
+    python tools/build_variants.py [--unit launch_tc|launch_gp_d3|...] NAME=FLAG[,FLAG...] ...
 Output: nmma_b200/lib/variants/lib_NAME.so (git-ignored, travels to the GPU box); select with NMMA_B200_LIB."""
 import os, subprocess, sys
 from concurrent.futures import ThreadPoolExecutor
@@ -8,18 +9,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as g
 g.build()
+UNIT = "launch_tc"
+if len(sys.argv) > 2 and sys.argv[1] == "--unit":
+    UNIT = sys.argv[2]
+    del sys.argv[1:3]
 VDIR = os.path.join(g.LIB_DIR, "variants")
 os.makedirs(VDIR, exist_ok=True)
 def one(spec):
     name, _, flags = spec.partition("=")
     defs = [f"-D{f}" for f in flags.split(",") if f]
-    obj = os.path.join(VDIR, f"launch_tc_{name}.o")
+    obj = os.path.join(VDIR, f"{UNIT}_{name}.o")
+    src, udefs, _ = g.UNITS[UNIT]
     extra = ["-DNMMA_DEV_BUILD"] if g.DEV else []
-    cmd = ["/usr/local/cuda/bin/nvcc"] + g.NVCC_FLAGS + extra + defs + ["-c", "-o", obj, os.path.join(g.CSRC, "launch_tc.cu")]
+    cmd = ["/usr/local/cuda/bin/nvcc"] + g.NVCC_FLAGS + extra + udefs + defs + ["-c", "-o", obj, os.path.join(g.CSRC, src)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode: print(r.stderr[-3000:]); raise SystemExit(1)
-    spills = [l.strip() for l in r.stderr.splitlines() if "spill" in l]
-    objs = [obj if u == "launch_tc" else g._obj(u) for u in g.UNITS]
+    spills = [l.strip() for l in r.stderr.splitlines() if "spill" in l or "Used" in l]
+    objs = [obj if u == UNIT else g._obj(u) for u in g.UNITS]
     lib = os.path.join(VDIR, f"lib_{name}.so")
     r = subprocess.run(["/usr/local/cuda/bin/nvcc", "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs, capture_output=True, text=True)
     if r.returncode: print(r.stderr[-3000:]); raise SystemExit(1)

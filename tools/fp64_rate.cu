@@ -10,7 +10,9 @@ __global__ void rate_kernel(int iters, double seed, double* sink, long long* cyc
     double a[CH];
     float b[CH];
     unsigned u[CH];
-    for (int i = 0; i < CH; ++i) { a[i] = seed + threadIdx.x + i; b[i] = (float)a[i]; u[i] = threadIdx.x * 7 + i; }
+    double b2[CH], c2[CH];
+    for (int i = 0; i < CH; ++i) { a[i] = seed + threadIdx.x + i; b[i] = (float)a[i]; u[i] = threadIdx.x * 7 + i;
+                                   b2[i] = 1.0 + 1e-12 * (threadIdx.x + i) * seed; c2[i] = 1e-9 * (threadIdx.x + 3 * i) * seed; }
     const double m = 1.0 + seed * 1e-12, c = seed * 1e-9;
     const float mf = (float)m, cf = (float)c;
     int cnt = 0;
@@ -25,6 +27,13 @@ __global__ void rate_kernel(int iters, double seed, double* sink, long long* cyc
             if (OP == 4) b[i] = fmaxf(b[i], cf + i);
             if (OP == 5) u[i] = (u[i] & 0xFFFFE000u) ^ (unsigned)it;
             if (OP == 6) a[i] = a[i] * m;
+            if (OP == 7) a[i] = fma(a[i], b2[i], c2[i]);                                   // three distinct register operands
+            if (OP == 8) { a[i] = fma(a[i], b2[i], c2[i]); u[i] = (u[i] & 0xFFFFE000u) ^ (unsigned)it; }   // + one LOP3 each
+            if (OP == 9) { a[i] = fma(a[i], m, c); u[i] = (u[i] & 0xFFFFE000u) ^ (unsigned)it; }
+            if (OP == 10) { a[i] = fma(a[i], m, c); if (i == 0) a[0] += (double)(int)(u[0] + it); }          // one I2F.F64 per 8 DFMA
+            if (OP == 11) a[0] = fma(a[0], m, c);                                          // one dependent chain: latency
+            if (OP == 12) a[i & 1] = fma(a[i & 1], m, c);                                  // two chains
+            if (OP == 13) a[i & 3] = fma(a[i & 3], m, c);                                  // four chains
         }
     }
     const long long t1 = clock64();
@@ -47,7 +56,7 @@ void run(const char* name, int warps_per_sm, int sms) {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
     const double winst = (double)iters * CH * warps_per_sm;  // per SM
-    printf("%-6s warps/SM %2d: %.3f warp-instr/clk/SM (%.1f clk per warp-instr per SMSP), %.2f T thread-op/s chip\n", name,
+    printf("%-11s warps/SM %2d: %.3f warp-instr/clk/SM (%.1f clk per warp-instr per SMSP), %.2f T thread-op/s chip\n", name,
            warps_per_sm, winst / c, c / (winst / 4.0), winst * 32.0 * sms / (ms * 1e-3) / 1e12);
     cudaFree(sink); cudaFree(cyc);
 }
@@ -59,6 +68,10 @@ int main() {
     for (int w : {4, 8, 16, 32}) {
         run<0>("DFMA", w, sms); run<1>("DADD", w, sms); run<6>("DMUL", w, sms); run<2>("DSETP", w, sms);
         run<3>("FFMA", w, sms); run<4>("FMNMX", w, sms); run<5>("LOP3", w, sms);
+    }
+    for (int w : {4, 8, 16}) {
+        run<7>("DFMA3r", w, sms); run<8>("DFMA3r+LOP", w, sms); run<9>("DFMA+LOP", w, sms); run<10>("DFMA+I2F/8", w, sms);
+        run<11>("DFMA chain1", w, sms); run<12>("DFMA chain2", w, sms); run<13>("DFMA chain4", w, sms);
     }
     return 0;
 }
