@@ -331,6 +331,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// Wait of a warp that is far ahead of its producer (back-end and TMA-producer warps of the tensor-core kernel): it leaves
+// the scheduler between polls, so its polling does not take issue slots from the activation warps of its sub-partition.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifdef TCV_MBAR_UNBOUNDED   // timing experiment (tools/build_variants.py)
     while (!mbar_try_wait(bar, parity)) {}

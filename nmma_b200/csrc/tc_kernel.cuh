@@ -205,6 +205,17 @@ struct TcBars {
     uint32_t finished;   // role warps that have left their loops
 };
 
+#ifdef TCV_SLEEP_PROD
+#define TC_WAIT_PROD(bar, par) mbar_wait_sleep(bar, par, TCV_SLEEP_PROD)
+#else
+#define TC_WAIT_PROD(bar, par) mbar_wait_spin(bar, par)
+#endif
+#ifdef TCV_SLEEP_BACK
+#define TC_WAIT_BACK(bar, par) mbar_wait_sleep(bar, par, TCV_SLEEP_BACK)
+#else
+#define TC_WAIT_BACK(bar, par) mbar_wait_spin(bar, par)
+#endif
+
 template <int K, bool FAST, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ out, int fsplit_arg) {
@@ -470,7 +481,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         int f = TC_PART_F0(item), f1 = TC_PART_F1(item);
         for (long long vv = 0; vv < total_v; ++vv, ++vseq) {
             const int slot = (int)(vseq & 1);
-            mbar_wait_spin(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
+            TC_WAIT_PROD(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&bars->b_full[slot], bbytes);
                 bulk_g2s(s_basis0 + slot * bslot, basis_src<FAST>(cfg, f, K), bbytes, &bars->b_full[slot]);
@@ -478,7 +489,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             __syncwarp();
             const float* src = cfg.tcpack + (size_t)f * NCH * kTcChunkFloats;
             for (int c = 0; c < NCH; ++c) {
-                mbar_wait_spin(&bars->w_free[st], ph ^ 1);
+                TC_WAIT_PROD(&bars->w_free[st], ph ^ 1);
                 if (elect_one()) {
 #ifdef TCV_NO_WLOAD
                     mbar_arrive(&bars->w_full[st]);
@@ -514,7 +525,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             for (int f = TC_PART_F0(item), f1 = TC_PART_F1(item); f < f1; ++f, ++vseq) {
                 const int slot = (int)(vseq & 1);
                 const uint32_t par = (vseq >> 1) & 1;
-                mbar_wait_spin(&bars->c_full[t][slot], par);
+                TC_WAIT_BACK(&bars->c_full[t][slot], par);
                 const float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
                 float cf[K];
 #pragma unroll
@@ -524,7 +535,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->c_free[t][slot]);
-                mbar_wait_spin(&bars->b_full[slot], par);
+                TC_WAIT_BACK(&bars->b_full[slot], par);
                 if (ok) {
                     const double* basis = reinterpret_cast<const double*>(s_basis0 + slot * bslot);
 #ifdef TCV_NO_BACKEND
