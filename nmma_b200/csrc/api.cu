@@ -86,7 +86,10 @@ int ensure_scratch(nmma_b200_t* h, size_t n_doubles) {
 }
 
 int launch_frontend(nmma_b200_t* h, const double* pts, long long N, double* coeff, cudaStream_t st) {
-    if (h->kind == 0) {
+    if (h->kind == 0 && h->tc_front_supported && N >= h->opt_tc_front_min && h->opt_path != 2) {
+        // "path" = 2 forces the plain two-stage kernels (parity tests compare the two front ends)
+        return launch_tc_coeff(h, pts, N, coeff, st);
+    } else if (h->kind == 0) {
         dim3 grid((unsigned)h->F, (unsigned)std::min<long long>(N, 32768));
         coeff_mlp_kernel<<<grid, kCoeffThreads, 0, st>>>(h->cfg, pts, N, coeff);
     } else {
@@ -308,6 +311,11 @@ int finalize(nmma_b200_t* h, bool need_obs) {
     // ---- observations + systematics ----
     h->fused_supported = false;
     h->tc_supported = false;
+    h->gp_fused_supported = false;
+    // coefficient mode of the tensor-core kernel: no observations needed (generate_lightcurve / coeffs use it too)
+    if (!h->have_obs) { c.G = 0; c.nobs = 0; }
+    h->tc_front_supported = (h->kind == 0) && K <= kTcN2 && c.tc_nch > 0 &&
+                            tc_smem_bytes(kTcN2, T, c.S, h->have_obs ? h->g_off[h->G] : 0) <= 227 * 1024;
     if (h->have_obs) {
         const int G = h->G;
         const int nobs = h->g_off[G];
@@ -881,6 +889,7 @@ int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     else if (k == "fused_min_points") h->opt_fused_min = value;
     else if (k == "tc_min_points") h->opt_tc_min = value;
     else if (k == "gp_min_points") h->opt_gp_min = value;
+    else if (k == "tc_front_min_points") h->opt_tc_front_min = value;
     else if (k == "max_ctas") h->opt_max_ctas = (int)value;
     else if (k == "pipeline_blocks") { if (value < 1 || value > 64) return fail(h, NMMA_B200_ERR_ARG, "pipeline_blocks must be 1..64"); h->opt_pipeline = (int)value; }
     else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }
@@ -901,6 +910,7 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
     else if (k == "ctas_per_sm") *value = h->last_ctas_per_sm;
     else if (k == "fused_supported") { if (int rc = finalize(h, true)) return rc; *value = h->fused_supported ? 1 : 0; }
     else if (k == "tc_supported") { if (int rc = finalize(h, true)) return rc; *value = h->tc_supported ? 1 : 0; }
+    else if (k == "tc_front_supported") { if (int rc = finalize(h, true)) return rc; *value = h->tc_front_supported ? 1 : 0; }
     else if (k == "gp_fused_supported") { if (int rc = finalize(h, true)) return rc; *value = h->gp_fused_supported ? 1 : 0; }
     else if (k == "algorithmic_flop_per_eval") {
         // F * [2 H (d + K) + 2 T K] (MLP) or Ntr*3d + F*K*Ntr*8 + F*2*T*K (GP)

@@ -61,6 +61,8 @@ struct nmma_b200_handle {
     nmma::DevCfg cfg{};
     bool fused_supported = false;
     bool tc_supported = false;
+    bool tc_front_supported = false;   // tensor-core front end in coefficient mode (any n_coeff <= 16, any filter mapping)
+    long long opt_tc_front_min = 128;  // two-stage path: coefficients from the tensor-core kernel from this batch size
     double* coeff_scratch = nullptr;
     double* tc_parts = nullptr;       // per-part sums of a filter-split tensor-core launch (launch_tc.cu)
     size_t tc_parts_cap = 0;
@@ -103,6 +105,7 @@ int fail(nmma_b200_t* h, int code, const char* fmt, ...);
 int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
 bool fused_has(int d, int K);
 int launch_tc(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
+int launch_tc_coeff(nmma_b200_t* h, const double* pts, long long N, double* coeff, cudaStream_t st);
 int launch_gp(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
 bool gp_fused_has(int d, int K);
 }  // namespace nmma

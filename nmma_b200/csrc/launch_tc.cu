@@ -60,6 +60,31 @@ int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cud
 }
 }  // namespace
 
+// Front end only: coefficients [N][F][K] (fp64) for the generic back end -- any n_coeff <= 16, any filter mapping.
+int launch_tc_coeff(nmma_b200_t* h, const double* pts, long long N, double* coeff, cudaStream_t st) {
+    constexpr int K = kTcN2;
+    const size_t smem = tc_smem_bytes(K, h->T, h->cfg.S, h->cfg.nobs);
+    static size_t attr_smem = 0;
+    if (attr_smem < smem) {
+        CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const long long super = (long long)kTcTile * kTcTiles;
+    const long long nsuper = (N + super - 1) / super;
+    long long grid = h->sm_count;
+    if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
+    int fsplit = 1;   // small batches: the filters of a super-tile over several CTAs (each part writes its own filters)
+    if (!h->opt_no_fsplit && nsuper * 2 <= grid) fsplit = (int)std::min<long long>(h->F, grid / nsuper);
+    grid = std::max<long long>(1, std::min(grid, nsuper * fsplit));
+    if (fsplit > 1) fused_tc_logl_kernel<K, false, true, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, fsplit);
+    else fused_tc_logl_kernel<K, false, false, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, 1);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->last_ctas_per_sm = 1;
+    return NMMA_B200_OK;
+}
+
 int launch_tc(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
     const bool fast = h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
     return fast ? launch_tc_f<true>(h, pts, N, out, st) : launch_tc_f<false>(h, pts, N, out, st);

@@ -216,7 +216,11 @@ struct TcBars {
 #define TC_WAIT_BACK(bar, par) mbar_wait_spin(bar, par)
 #endif
 
-template <int K, bool FAST, bool SPLIT>
+// COEFF = true: front end only.  The back-end warps write the coefficients [N][F][cfg.K] (fp64, + b2) to `out` instead of
+// scoring them: the generic back end (backend_logl_kernel / backend_mags_kernel) follows in a second launch.  This is the
+// path of configurations the fused back end does not cover (averaged filters, n_coeff != 10): K is then the padded
+// width kTcN2 and cfg.K the real one.
+template <int K, bool FAST, bool SPLIT, bool COEFF = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ out, int fsplit_arg) {
     const int fsplit = SPLIT ? fsplit_arg : 1;   // SPLIT = false: the throughput instantiation, index arithmetic folds away
@@ -239,6 +243,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int F = cfg.F, NCH = cfg.tc_nch;
+    const int Kr = COEFF ? cfg.K : K;   // real n_coeff
     constexpr int SUPER = kTcTile * kTcTiles;
     const long long nsuper = ((N + SUPER - 1) / SUPER) * fsplit;   // work items
     const long long my_super = (nsuper > blockIdx.x) ? (nsuper - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -384,7 +389,8 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 mbar_wait_spin(&bars->c_free[t][slot], ((vseq >> 1) & 1) ^ 1);
                 float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
 #pragma unroll
-                for (int k = 0; k < K; ++k) cb[k * kTcTile] = okx ? acc[k] + cfg.b2[f * K + k] : CUDART_NAN_F;
+                for (int k = 0; k < K; ++k)
+                    if (!COEFF || k < Kr) cb[k * kTcTile] = okx ? acc[k] + cfg.b2[f * Kr + k] : CUDART_NAN_F;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->c_full[t][slot]);
             }
@@ -481,12 +487,14 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         int f = TC_PART_F0(item), f1 = TC_PART_F1(item);
         for (long long vv = 0; vv < total_v; ++vv, ++vseq) {
             const int slot = (int)(vseq & 1);
-            TC_WAIT_PROD(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&bars->b_full[slot], bbytes);
-                bulk_g2s(s_basis0 + slot * bslot, basis_src<FAST>(cfg, f, K), bbytes, &bars->b_full[slot]);
+            if constexpr (!COEFF) {
+                TC_WAIT_PROD(&bars->b_free[slot], ((vseq >> 1) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bars->b_full[slot], bbytes);
+                    bulk_g2s(s_basis0 + slot * bslot, basis_src<FAST>(cfg, f, K), bbytes, &bars->b_full[slot]);
+                }
+                __syncwarp();
             }
-            __syncwarp();
             const float* src = cfg.tcpack + (size_t)f * NCH * kTcChunkFloats;
             for (int c = 0; c < NCH; ++c) {
                 TC_WAIT_PROD(&bars->w_free[st], ph ^ 1);
@@ -519,6 +527,23 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             const long long n = (item / fsplit) * SUPER + (long long)t * kTcTile + pidx;
             const bool live = n < N;
             const double* row = pts + (live ? n : 0) * cfg.P;
+            if constexpr (COEFF) {
+                for (int f = TC_PART_F0(item), f1 = TC_PART_F1(item); f < f1; ++f, ++vseq) {
+                    const int slot = (int)(vseq & 1);
+                    TC_WAIT_BACK(&bars->c_full[t][slot], (vseq >> 1) & 1);
+                    const float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
+                    if (live) {
+                        double* dst = out + ((size_t)n * F + f) * Kr;
+                        for (int k = 0; k < Kr; ++k) dst[k] = (double)cb[k * kTcTile];
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&bars->c_free[t][slot]);
+                        atomicAdd(&bars->progress, 1u);
+                    }
+                }
+                continue;
+            }
             const PointScal ps = point_setup(cfg, row);
             bool ok = !ps.bad && !cfg.static_fail;
             double logl = 0.0;
@@ -576,7 +601,8 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         uint32_t last = *prog;
         unsigned long long t_last = global_timer_ns();
         while (*fin < (uint32_t)(kTcThreads / 32 - 1)) {
-            __nanosleep(20000);
+            __nanosleep(500);   // short: the CTA cannot retire before this warp has seen `finished` (a 20 us nap cost a
+                                // one-point call 26 us, tools/latency.py)
             const uint32_t p = *prog;
             const unsigned long long now = global_timer_ns();
             if (p != last) { last = p; t_last = now; }

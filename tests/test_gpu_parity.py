@@ -375,6 +375,46 @@ def test_averaged_filters(torch_cuda):
     assert eng.get_info("fused_supported") == 0
     got = lik.log_likelihood_batch(pts, cols)
     print("averaged", assert_logl_close(got, ref))
+    # From 128 points the coefficients come from the tensor-core kernel in coefficient mode (tcgen05 front end + generic
+    # back end, launch_tc.cu: launch_tc_coeff); "path" = 2 keeps the plain two-stage kernels for comparison
+    assert eng.get_info("tc_front_supported") == 1
+    big, _ = priors.sample_array(256 * 3 + 77, np.random.default_rng(14), cols)          # filter-split and ragged tile
+    big[3, cols.index("KNtheta")] = np.nan
+    auto = eng.logl_host(big)
+    eng.set_option("path", 2); plain = eng.logl_host(big); eng.set_option("path", 0)
+    assert plain[3] == SENTINEL and auto[3] == SENTINEL
+    print("averaged, tensor-core front end vs plain two-stage", assert_logl_close(auto, plain))
+    ref_big = harness.oracle_logl(olik, fixed, big[:64], cols)
+    assert_logl_close(auto[:64], ref_big)
+    huge, _ = priors.sample_array(40_000, np.random.default_rng(15), cols)               # un-split instantiation
+    a2 = eng.logl_host(huge)
+    eng.set_option("path", 2); p2 = eng.logl_host(huge[:2000]); eng.set_option("path", 0)
+    assert_logl_close(a2[:2000], p2)
+    c_tc = eng.coeffs(huge[:4096]).cpu().numpy()
+    eng.set_option("path", 2); c_plain = eng.coeffs(huge[:4096]).cpu().numpy(); eng.set_option("path", 0)
+    assert np.abs(c_tc - c_plain).max() < 2e-5 * max(1.0, np.abs(c_plain).max())
+
+
+def test_n_coeff_other_than_ten(torch_cuda):
+    """n_coeff = 7: no fused instantiation; coefficients from the tensor-core kernel in coefficient mode (any K <= 16)."""
+    from oracle import harness
+    from nmma_b200 import synthetic as syn
+    from nmma_b200.mlmodel import random_surrogate
+    filters = ["ps1::g", "ps1::r", "2massks"]
+    mins, maxs = syn.GRID_BOUNDS["Bu2019lm"]
+    core = random_surrogate(filters, d=4, kind="mlp", seed=5, K=7, H=512, param_mins=mins, param_maxs=maxs)
+    rng = np.random.default_rng(3)
+    lc_data = synthetic_observations(filters, rng, n_per_filter=9, tmax=12.0, n_ul=1, mag0=18.0, slope=0.3)
+    priors = syn.bu2019lm_prior()
+    lik, olik, fixed, cols = build_pair(core, "Bu2019lm", filters, filters, lc_data, priors)
+    eng = lik.sub_model.engine_for(cols)
+    assert eng.get_info("fused_supported") == 0 and eng.get_info("tc_supported") == 0 and eng.get_info("tc_front_supported") == 1
+    pts, _ = priors.sample_array(1000, np.random.default_rng(4), cols)
+    ref = harness.oracle_logl(olik, fixed, pts[:100], cols)
+    got = eng.logl_host(pts)
+    assert_logl_close(got[:100], ref)
+    eng.set_option("path", 2); plain = eng.logl_host(pts); eng.set_option("path", 0)
+    print("n_coeff 7", assert_logl_close(got, plain))
 
 
 def test_obs_term_edge_semantics(torch_cuda):

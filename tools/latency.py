@@ -5,8 +5,8 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, bench
-wl = bench.build_workload(); cols = list(wl["priors"].keys())
-lik, model, handler = bench.gpu_likelihood(wl, 0)
+wl = bench.make_spec("c2"); cols = wl["cols"]
+lik = bench.gpu_likelihood(wl, 0)
 pts, _ = wl["priors"].sample_array(4096, np.random.default_rng(3), cols)
 dicts = [dict(zip(cols, row)) for row in pts[:2000]]
 for d in dicts[:50]: lik.log_likelihood(d)

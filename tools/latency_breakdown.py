@@ -4,8 +4,8 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, bench
-wl = bench.build_workload(); cols = list(wl["priors"].keys())
-lik, model, handler = bench.gpu_likelihood(wl, 0)
+wl = bench.make_spec("c2"); cols = wl["cols"]
+lik = bench.gpu_likelihood(wl, 0)
 eng = lik.sub_model.engine_for(cols)
 pts, _ = wl["priors"].sample_array(64, np.random.default_rng(3), cols)
 row = np.ascontiguousarray(pts[:1]); out = np.empty(1)
