@@ -154,6 +154,58 @@ def _cpu_eval(task):
     return harness.oracle_logl(lik, fixed, chunk, _SPECS[name]["cols"])
 
 
+# The reference's OWN classes, when a copy of the package travels with the repository (baseline/_ref/nmma: `pip install
+# --no-deps --target baseline/_ref /root/reference`, git-ignored).  Third-party modules that are absent
+# offline are stubbed exactly as for the golden vectors (tests/golden/reference_stubs.py: Keras forward pass = fp32
+# NumPy on the same weights, astropy Planck18 = the flat-LCDM integral); every line of nmma/em/{model,em_likelihood,
+# systematics,utils,lightcurve_generation}.py and nmma/core/{base,conversion}.py runs unmodified.
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+_REFLIKS = {}
+
+
+def reference_classes_available():
+    return os.path.isfile(os.path.join(REF_DIR, "nmma", "em", "em_likelihood.py"))
+
+
+def _reference_lik_for(name):
+    if name not in _REFLIKS:
+        import tempfile
+        import joblib
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import reference_stubs as RS
+        from oracle.nmma_oracle import KerasStandIn
+        RS.REF = REF_DIR
+        mods = RS.load_reference()
+        s = _SPECS[name]
+        assert s["kind"] == "mlp"
+        filters = list(s["filters"])
+        tmp = tempfile.mkdtemp(prefix="nmma_ref_model_")
+        # the surrogate in the reference's on-disk layout: {model}.joblib (SVD basis per filter) + {model}_tf/{filter}.keras
+        # (placeholder files: the stubbed keras.saving.load_model hands out the in-memory weights of the workload)
+        meta = {f.replace(":", "_"): {k: v for k, v in s["core"][f].items() if k != "model"} for f in filters}
+        joblib.dump(meta, os.path.join(tmp, f"{s['model']}.joblib"))
+        os.makedirs(os.path.join(tmp, f"{s['model']}_tf"))
+        weights = {}
+        for f in filters:
+            fn = os.path.join(tmp, f"{s['model']}_tf", f.replace(":", "_") + ".keras")
+            open(fn, "w").close()
+            weights[fn] = s["core"][f]["model"]
+        sys.modules["keras.saving"].load_model = lambda fn, compile=False: KerasStandIn(*weights[fn])
+        model = mods["model"].SVDLightCurveModel(s["model"], svd_path=tmp, interpolation_type="tensorflow",
+                                                 filters=filters, local_only=True)
+        handler = mods["systematics"].FilterSystematicsHandler(filters, None, 1.0, s["lc_data"][0])
+        _REFLIKS[name] = mods["em_likelihood"].EMTransientLikelihood(model, s["lc_data"], handler, s["priors"],
+                                                                     filters=filters, detection_limit=s["limit"])
+    return _REFLIKS[name]
+
+
+def _ref_eval(task):
+    name, chunk = task
+    lik = _reference_lik_for(name)
+    cols = _SPECS[name]["cols"]
+    return np.array([lik.log_likelihood(dict(zip(cols, map(float, row)))) for row in chunk])
+
+
 class CpuArm:
     """multiprocessing pool over the host cores (the analogue of the reference's schwimmbad task farm,
     nmma/core/mpi_setup.py:651-683); workers are forked before CUDA is initialised."""
@@ -163,12 +215,12 @@ class CpuArm:
         self.cores = cores or len(os.sched_getaffinity(0))
         self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init)
 
-    def run(self, name, pts, parts=None):
+    def run(self, name, pts, parts=None, reference_classes=False):
         if len(pts) == 0:
             return np.zeros(0), 0.0
         chunks = np.array_split(pts, min(len(pts), parts or self.cores * 4))
         t0 = time.perf_counter()
-        out = np.concatenate(self.pool.map(_cpu_eval, [(name, c) for c in chunks]))
+        out = np.concatenate(self.pool.map(_ref_eval if reference_classes else _cpu_eval, [(name, c) for c in chunks]))
         return out, time.perf_counter() - t0
 
     def close(self):
@@ -227,43 +279,53 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm
 # ---------------------------------------------------------------------------------------------
+REFERENCE_WHAT = ("the reference's own classes (nmma.em.model.SVDLightCurveModel + nmma.em.em_likelihood.EMTransientLikelihood."
+                  "log_likelihood(dict) per point, unmodified source from baseline/_ref; absent third-party modules stubbed: "
+                  "Keras forward pass = fp32 NumPy on the same weights, astropy Planck18 = flat-LCDM integral)")
+PORT_WHAT = ("the per-point NumPy/SciPy oracle port of the reference (fp32 NumPy MLP standing in for Keras; baseline/_ref "
+             "absent)")
+
+
 def reference_arm(args):
     """The reference's own CPU implementation of the path on all host cores; each step is a bounded sample of the
-    workload.  The real package cannot be imported offline (bilby, sncosmo, astropy, tensorflow absent -- DESIGN.md), so the
-    per-point path runs through the oracle PORT (same NumPy / SciPy / sklearn calls, fp32 NumPy MLP standing in for the
-    Keras call); the port reproduces the reference's own source files to 1e-15 on the committed vectors
-    (tests/test_reference_vectors.py)."""
+    workload.  When the reference package travels with the repository (baseline/_ref/nmma, see REF_DIR) its OWN classes
+    run, with the third-party modules that are absent offline (bilby, sncosmo, astropy, keras) stubbed as for the golden
+    vectors; otherwise the oracle PORT (same NumPy / SciPy / sklearn calls), which reproduces the reference's source files
+    to 1e-15 on the committed vectors (tests/test_reference_vectors.py).  The line says which one ran (`cpu_baseline.kind`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     _SPECS["c2"] = make_spec("c2")
     spec = _SPECS["c2"]
     arm = CpuArm()
+    refcls = reference_classes_available()
     rng = np.random.default_rng(1234)
     probe, _ = spec["priors"].sample_array(arm.cores * 40, rng, spec["cols"])
-    _, dt = arm.run("c2", probe)
+    arm.run("c2", probe, reference_classes=refcls)         # builds the likelihood in every worker
+    _, dt = arm.run("c2", probe, reference_classes=refcls)
     rate = len(probe) / dt
     # bounded sample: ~4 s of CPU work per step, shrunk so that steps + warm-up stay within ~2 minutes whatever K is
     sec_per_step = min(4.0, max(0.2, 120.0 / max(1, args.steps + args.warmup)))
     per_step = int(max(arm.cores * 40, min(rate * sec_per_step, 200000)))
     pts, _ = spec["priors"].sample_array(per_step, rng, spec["cols"])
     for _ in range(args.warmup):
-        arm.run("c2", pts)
+        arm.run("c2", pts, reference_classes=refcls)
     t = 0.0
     for _ in range(args.steps):
-        _, dt = arm.run("c2", pts)
+        _, dt = arm.run("c2", pts, reference_classes=refcls)
         t += dt
     arm.close()
     value = per_step * args.steps / t
-    sample = (f"{per_step} prior draws per step through the per-point Python path (NumPy/SciPy oracle port of the reference, "
-              "fp32 NumPy MLP standing in for Keras), multiprocessing pool on all host cores")
+    sample = (f"{per_step} prior draws per step through " + (REFERENCE_WHAT if refcls else PORT_WHAT) +
+              ", multiprocessing pool on all host cores")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 MLP / f64 likelihood",
         "data": "synthetic weights, real AT2017gfo photometry",
         "config": {"workload": WORKLOAD, "points_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "reference" if refcls else "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -318,17 +380,19 @@ def gpu_arm(args):
         if world == 1 and not args.no_cpu:
             s = _SPECS["c2"]
             rng = np.random.default_rng(99)
+            refcls = reference_classes_available()
             probe, _ = s["priors"].sample_array(arm.cores * 40, rng, s["cols"])
-            _, dt = arm.run("c2", probe)
+            arm.run("c2", probe, reference_classes=refcls)                             # builds the likelihood in every worker
+            _, dt = arm.run("c2", probe, reference_classes=refcls)
             n_s = int(max(arm.cores * 40, min(len(probe) / dt * 12.0, 400000)))      # ~12 s of CPU work
             cpu_pts, _ = s["priors"].sample_array(n_s, rng, s["cols"])
-            _, dt = arm.run("c2", cpu_pts)
+            _, dt = arm.run("c2", cpu_pts, reference_classes=refcls)
             t0 = time.perf_counter()
-            arm.run("c2", cpu_pts[:300], parts=1)
+            arm.run("c2", cpu_pts[:300], parts=1, reference_classes=refcls)
             one_core = 300 / (time.perf_counter() - t0)
-            cpu = {"value": n_s / dt, "unit": UNIT, "cores": arm.cores, "kind": "port",
-                   "sample": f"{n_s} draws of the same prior through the per-point NumPy/SciPy oracle port of the reference "
-                             f"(fp32 NumPy MLP standing in for Keras), multiprocessing pool on all host cores",
+            cpu = {"value": n_s / dt, "unit": UNIT, "cores": arm.cores, "kind": "reference" if refcls else "port",
+                   "sample": f"{n_s} draws of the same prior through " + (REFERENCE_WHAT if refcls else PORT_WHAT) +
+                             ", multiprocessing pool on all host cores",
                    "one_core_value": one_core, "cpu_count": os.cpu_count()}
         for name in names:
             if name == "c5":
