@@ -434,6 +434,31 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //     from the float2 row-pair pack (cfg.bpack32): ~1e-5 mag, the size of the fp32 MLP's own rounding noise.
 //   * Gaussian term of a plain detection in fp32, summed over observations and filters in fp64; upper limits,
 //     finite detection limits and sampled systematics go through the fp64 obs_term with the same mu.
+// log Phi(b) in fp32 for the FAST back end (the truncation mass of a detection below a finite limit,
+// em_likelihood.py:252-256 through truncnorm._log_gauss_mass).  log(erfc(y) / 2), y = |b| / sqrt 2, from the Chebyshev fit of
+// Numerical Recipes' erfcc -- erfc(y) = t exp(-y^2 + P(t)), t = 1 / (1 + y / 2), fractional error < 1.2e-7 for every y >= 0 --
+// taken in the log domain, so the left tail needs no exp and no asymptotic branch; for b > 0, log(1 - p) with p = erfc / 2:
+// -p - p^2 / 2 below 1e-3, MUFU log otherwise.  Error < 4e-7 max(1, |log Phi|) against scipy.special.log_ndtr (restated in fp32
+// in tests/test_round2_cpu.py::test_fast_log_ndtr_restatement; on the device through the finite-limit parity tests).
+__device__ __forceinline__ float fast_log_ndtr(float b) {
+    const float y = fabsf(b) * 0.70710678f;
+    const float t = __frcp_rn(fmaf(0.5f, y, 1.0f));
+    float p = fmaf(t, 0.17087277f, -0.82215223f);
+    p = fmaf(p, t, 1.48851587f);
+    p = fmaf(p, t, -1.13520398f);
+    p = fmaf(p, t, 0.27886807f);
+    p = fmaf(p, t, -0.18628806f);
+    p = fmaf(p, t, 0.09678418f);
+    p = fmaf(p, t, 0.37409196f);
+    p = fmaf(p, t, 1.00002368f);
+    p = fmaf(p, t, -1.26551223f);
+    const float lg = __logf(0.5f * t) + fmaf(-y, y, p);      // log(erfc(y) / 2) = log Phi(-|b|)
+    if (!(b > 0.f)) return lg;                                // NaN propagates
+    if (b > 8.3f) return 0.f;                                 // Phi(-8.3) < 2^-53
+    const float q = __expf(lg);                               // 1 - Phi(b)
+    return (q < 1e-3f) ? -q * fmaf(0.5f, q, 1.0f) : __logf(1.0f - q);
+}
+
 template <int K, bool FAST, typename CT>
 __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, const CT (&cp)[K], const PointScal& ps,
                                                     const double* __restrict__ row, const double* __restrict__ bp,
@@ -524,19 +549,13 @@ __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, co
                     const float s2 = fmaf(ssys, ssys, sl.x);
                     const float inv = rsqrtf(s2);
                     const float xq = (rf.y - mu) * inv;
-                    float term = fmaf(-0.5f * xq, xq, -0.5f * logf(s2) - (float)NMMA_NORM_PDF_LOGC);
+                    // log(s2) through MUFU.LG2 (__logf: absolute error < 4e-7 for s2 of order one) -- the libm forms of
+                    // this class (logf, erfcf, log1pf) were ~300 instructions per observation and made the back end
+                    // the critical path of config 3 (profiles/r02_fused_tc_c3_summary.json)
+                    float term = fmaf(-0.5f * xq, xq, -0.5f * __logf(s2) - (float)NMMA_NORM_PDF_LOGC);
                     if (sl.y < CUDART_INF_F) {   // truncation at the detection limit: - log Phi((lim - mu) / sigma)
                         const float bq = (sl.y - mu) * inv;
-                        float mass = 0.f;                                                  // log Phi(bq); Phi(-8.3) < 2^-53
-                        if (bq > 0.f) {
-                            if (bq < 8.3f) mass = log1pf(-0.5f * erfcf(bq * 0.70710678f));
-                        } else if (bq > -12.f) {
-                            mass = logf(0.5f * erfcf(-bq * 0.70710678f));
-                        } else {   // log_ndtr's asymptotic series (scipy/special/_log_ndtr: -b^2/2 - log(-b) - log(2 pi)/2 + log(1 - 1/b^2 + 3/b^4))
-                            const float r2 = 1.0f / (bq * bq);
-                            mass = fmaf(-0.5f * bq, bq, -logf(-bq) - (float)NMMA_NORM_PDF_LOGC) + log1pf(r2 * (3.0f * r2 - 1.0f));
-                        }
-                        term -= mass;
+                        term -= fast_log_ndtr(bq);
                     }
                     general = general || !(s2 > 0.f) || !(s2 < CUDART_INF_F);
                     if (!general) lsum += (double)term;

@@ -63,7 +63,10 @@ constexpr uint32_t kColD1 = 0;               // 2 x 64  layer-1 accumulators, ov
 constexpr uint32_t kColA2L = 128;            // 2 x 32  h_lo as fp16 pairs (column j = hidden units 2j, 2j+1)
 constexpr uint32_t kColD2 = 192;             // 2 x 16  layer-2 h_hi*W_hi partials, double buffered by accumulation group
 constexpr uint32_t kColD2X = 240;            // 16      layer-2 cross terms h_lo*W_hi + h_hi*W_lo of the whole filter
-constexpr int kTcGroup = 2;                  // chunks per layer-2 accumulation chain (12 MMAs, RZ accumulate)
+#ifndef TCV_GROUP
+#define TCV_GROUP 2
+#endif
+constexpr int kTcGroup = TCV_GROUP;          // chunks per layer-2 accumulation chain (8 k-step MMAs each, RZ accumulate)
 constexpr uint32_t kColA1H = 224;            // 8       [x_hi, 1, 0..]
 constexpr uint32_t kColA1L = 232;            // 8       [x_lo, 0, 0..]
 
@@ -377,6 +380,12 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 tc_fence_after();
                 {
                     uint32_t part[16], cr[16];
+                    if constexpr (kTcGroup == 1) {   // one chunk per chain: the partial of chunk NCH - 2 is still unread too
+                        tmem_ld16(tbase + kColD2 + 16 * ((NCH - 2) & 1), part);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
+                    }
                     tmem_ld16(tbase + kColD2 + 16 * (((NCH - 1) / kTcGroup) & 1), part);
                     tmem_ld16(tbase + kColD2X, cr);
                     tmem_wait_ld();

@@ -185,7 +185,10 @@ def test_mlp_fp32_accuracy_vs_fp64_truth(torch_cuda):
     rng = np.random.default_rng(2)
     x = rng.uniform([-2.0, -2.0, 0.0], [-1.05, -1.05, 90.0], size=(256, 3))
     pts = np.concatenate([x, np.full((256, 1), 40.0), np.zeros((256, 3))], axis=1)   # [x, dL, timeshift, redshift, Ebv]
+    eng.set_option("path", 2)                      # plain two-stage kernels: fp32 FFMA front end (coeff_mlp_kernel)
     got = eng.coeffs(pts).cpu().numpy()
+    eng.set_option("path", 0)                      # >= 128 points: the tensor-core kernel in coefficient mode (3xTF32 split)
+    got_tc = eng.coeffs(pts).cpu().numpy()
     for fi, f in enumerate(filters):
         W1, b1, W2, b2 = core[f]["model"]
         xs = ((x - core[f]["param_mins"]) / (core[f]["param_maxs"] - core[f]["param_mins"])).astype(np.float32)
@@ -193,8 +196,13 @@ def test_mlp_fp32_accuracy_vs_fp64_truth(torch_cuda):
         npf32 = np.maximum(xs @ W1 + b1, np.float32(0)) @ W2 + b2
         e_gpu = np.abs(got[:, fi, :] - exact).max()
         e_np = np.abs(npf32 - exact).max()
-        print(f, "gpu fp32 err", e_gpu, "numpy fp32 err", e_np)
+        e_tc = np.abs(got_tc[:, fi, :] - exact).max()
+        print(f, "gpu fp32 err", e_gpu, "numpy fp32 err", e_np, "tensor-core 3xTF32 err", e_tc)
         assert e_gpu < 2e-5 and e_gpu < 4 * e_np + 1e-6
+        # 3xTF32 drops the lo x lo products and the tensor core accumulates with round-toward-zero (group partials are
+        # added with RN on the CUDA cores): ~1e-5 absolute on these trained weights (coefficients of order 1-10), i.e.
+        # < 1e-4 mag through (maxs - mins) VA -- a factor 10 inside the 1e-3 mag budget, a factor 6 above fp32 FFMA
+        assert e_tc < 3e-5
 
 
 # ------------------------------------------------------------------------------------------------

@@ -216,3 +216,25 @@ def test_create_prior_from_args(tmp_path):
                 dict(fits_file="x.fits")):
         with pytest.raises(NotImplementedError):
             create_prior_from_args(SimpleNamespace(prior=str(pf), use_Ebv=False, Ebv_max=0.5, **bad), None)
+
+
+def test_fast_log_ndtr_restatement():
+    """csrc/kernels.cuh: fast_log_ndtr (log Phi(b) of the FAST back end's finite-detection-limit class) restated operation
+    by operation in fp32 NumPy and checked against scipy.special.log_ndtr: pins the Chebyshev coefficients (Numerical
+    Recipes erfcc, taken in the log domain), the 1e-3 switch and the 8.3 cut-off."""
+    from scipy.special import log_ndtr
+    f = np.float32
+    b = np.linspace(-40.0, 9.0, 200001).astype(f)
+    y = np.abs(b) * f(0.70710678)
+    t = (f(1) / (f(0.5) * y + f(1))).astype(f)
+    coef = [0.17087277, -0.82215223, 1.48851587, -1.13520398, 0.27886807, -0.18628806, 0.09678418, 0.37409196, 1.00002368,
+            -1.26551223]
+    p = f(coef[0])
+    for c in coef[1:]:
+        p = (p * t + f(c)).astype(f)
+    lg = (np.log((f(0.5) * t).astype(f)).astype(f) + (p - y * y).astype(f)).astype(f)
+    q = np.exp(lg).astype(f)
+    pos = np.where(q < 1e-3, -q * (1 + f(0.5) * q), np.log((1 - q).astype(f))).astype(f)
+    got = np.where(b > 0, np.where(b > 8.3, 0.0, pos), lg)
+    ref = log_ndtr(b.astype(np.float64))
+    assert (np.abs(got - ref) / np.maximum(1.0, np.abs(ref))).max() < 6e-7
