@@ -250,8 +250,9 @@ int nmma_b200_logl_sweep(nmma_b200_t* h, uint64_t seed, int64_t first_index, int
                          double* out_dev, double* points_dev, void* stream);
 
 /* ---- knobs / introspection ------------------------------------------- */
-/* keys: "path" (0 auto, 1 fused FFMA kernel, 2 two-stage front end + back end, 3 tensor-core kernel, 4 fused GP kernel),
- *       "tc_min_points" / "fused_min_points" / "gp_min_points" / "tc_front_min_points" (thresholds of the automatic path), "max_ctas" (0 = one per SM),
+/* keys: "path" (0 auto, 1 fused FFMA kernel, 2 two-stage front end + back end, 3 tensor-core kernel, 4 fused GP kernel,
+ *       5 latency path: tensor-core kernel in coefficient mode with filters and hidden ranges over all SMs + back end),
+ *       "tc_min_points" / "fused_min_points" / "gp_min_points" / "tc_front_min_points" / "latency_max_points" (thresholds of the automatic path), "max_ctas" (0 = one per SM),
  *       "points_per_thread" (FFMA kernel: 0 auto, 1, 2, 4), "no_fast_backend" (1 = generic fp64 back end),
  *       "no_filter_split" (1 = tensor-core kernel keeps one CTA per 256-point super-tile on small batches),
  *       "pipeline_blocks" (row blocks of the nmma_b200_logl_host copy/compute pipeline, 1 = serial),

@@ -703,8 +703,11 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "tensor-core kernel unavailable for this configuration (GP path, averaged filters, d > 7 or n_coeff != 10)");
     if (path == 4 && !h->gp_fused_supported)
         return fail(h, NMMA_B200_ERR_UNSUPPORTED, "fused GP kernel unavailable for this configuration (MLP path, averaged filters, d outside 2..7, n_coeff != 10 or alpha > 1e5)");
+    if (path == 5 && !h->tc_front_supported)
+        return fail(h, NMMA_B200_ERR_UNSUPPORTED, "latency path unavailable for this configuration (GP path, d > 7 or n_coeff > 16)");
     if (path == 0) {
-        if (h->tc_supported && N >= h->opt_tc_min) path = 3;
+        if (h->tc_front_supported && N <= h->opt_latency_max) path = 5;
+        else if (h->tc_supported && N >= h->opt_tc_min) path = 3;
         else if (h->gp_fused_supported && N >= h->opt_gp_min) path = 4;
         else path = (h->fused_supported && N >= h->opt_fused_min) ? 1 : 2;
     }
@@ -712,6 +715,26 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
     if (path == 3) return launch_tc(h, points_dev, N, out_dev, st);
     if (path == 1) return launch_fused(h, points_dev, N, out_dev, st);
     if (path == 4) return launch_gp(h, points_dev, N, out_dev, st);
+    if (path == 5) {
+        // one point per call / small batches: filters and hidden ranges of each super-tile over all SMs (fp32 partial
+        // coefficient sums), then one warp per point adds and scores them -- 2 launches
+        const size_t FK = (size_t)h->F * h->K;
+        if (int rc = ensure_scratch(h, (size_t)N * FK * 16 / 2 + 16)) return rc;   // <= 16 hidden ranges of fp32
+        int hsplit = 1;
+        float* parts = reinterpret_cast<float*>(h->coeff_scratch);
+        if (int rc = launch_tc_coeff_parts(h, points_dev, N, parts, &hsplit, st)) return rc;
+        const long long wpb = kBackThreads / 32;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((N + wpb - 1) / wpb, (long long)h->sm_count * 16));
+        // FAST per-observation terms (lanes over observations) where the fused kernels would use them too; else generic fp64
+        const bool fast = h->tc_supported && h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
+        if (fast) backend_logl_parts_fast_kernel<10><<<(unsigned)std::min<long long>(N, (long long)h->sm_count * 8), kLatThreads,
+                                                        ((FK + 1) & ~size_t(1)) * sizeof(float) + (kLatThreads / 32) * sizeof(double), st>>>(
+                      h->cfg, points_dev, parts, hsplit, N, out_dev);
+        else backend_logl_parts_kernel<<<grid, kBackThreads, wpb * FK * sizeof(double), st>>>(h->cfg, points_dev, parts, hsplit, N, out_dev);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        return NMMA_B200_OK;
+    }
     const size_t FK = (size_t)h->F * h->K;
     const long long chunk = std::min<long long>(N, kTwoStageChunk);
     if (int rc = ensure_scratch(h, (size_t)chunk * FK)) return rc;
@@ -782,6 +805,13 @@ static int logl_host_impl(nmma_b200_t* h, const double* points_host, int64_t N, 
         // calls and their DMA round trips from a call whose kernels take ~40 us (tools/latency_breakdown.py)
         const double* src = points_host;
         if (!in_pinned) { std::memcpy(h->stage_in_host, points_host, nin * sizeof(double)); src = h->stage_in_host; }
+        // The latency path (path 5) reads each row from hundreds of threads in ~150 CTAs: over PCIe that costs more than
+        // it saves (73 vs 60 us per one-point call), so its rows are copied (one small DMA); the result is still written in
+        // place.  The filter-split fused kernel (9 CTAs, one reader per point) keeps reading in place.
+        if (h->tc_front_supported && N <= h->opt_latency_max && (h->opt_path == 0 || h->opt_path == 5)) {
+            CU(cudaMemcpyAsync(h->stage_in_dev, src, nin * sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
+            src = h->stage_in_dev;
+        }
         if (int rc = nmma_b200_logl(h, src, N, dst, h->own_stream)) return rc;
         CU(cudaStreamSynchronize(h->own_stream));
     } else if (nblk == 1) {
@@ -885,11 +915,12 @@ int nmma_b200_mags(nmma_b200_t* h, const double* points_dev, int64_t N, int appa
 int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     if (!h || !key) return NMMA_B200_ERR_ARG;
     const std::string k(key);
-    if (k == "path") { if (value < 0 || value > 4) return fail(h, NMMA_B200_ERR_ARG, "path must be 0 (auto), 1 (fused FFMA), 2 (two-stage), 3 (tensor core) or 4 (fused GP)"); h->opt_path = (int)value; }
+    if (k == "path") { if (value < 0 || value > 5) return fail(h, NMMA_B200_ERR_ARG, "path must be 0 (auto), 1 (fused FFMA), 2 (two-stage), 3 (tensor core), 4 (fused GP) or 5 (latency: hidden-split tensor core + back end)"); h->opt_path = (int)value; }
     else if (k == "fused_min_points") h->opt_fused_min = value;
     else if (k == "tc_min_points") h->opt_tc_min = value;
     else if (k == "gp_min_points") h->opt_gp_min = value;
     else if (k == "tc_front_min_points") h->opt_tc_front_min = value;
+    else if (k == "latency_max_points") h->opt_latency_max = value;
     else if (k == "max_ctas") h->opt_max_ctas = (int)value;
     else if (k == "pipeline_blocks") { if (value < 1 || value > 64) return fail(h, NMMA_B200_ERR_ARG, "pipeline_blocks must be 1..64"); h->opt_pipeline = (int)value; }
     else if (k == "packed_fma") { /* kept for compatibility: two points per thread always use FFMA2 */ }

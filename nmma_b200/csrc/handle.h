@@ -86,6 +86,8 @@ struct nmma_b200_handle {
     long long opt_tc_min = 1;         // tensor-core path from the first point: with the filters of a super-tile split over CTAs
                                       // (launch_tc.cu) one call takes 39 us at N = 1 and 40-46 us up to 4096 points, the two-stage
                                       // kernels 47 us + 0.6 us per point (tools/latency_breakdown.py, tools/latency.py)
+    long long opt_latency_max = 1024; // up to this batch size the hidden layer is split over CTAs too (path 5: launch_tc_coeff_parts +
+                                      // backend_logl_parts_kernel); above, the filter-split fused kernel (path 3)
     long long opt_gp_min = 4096;      // fused GP kernel (thread = point) from this batch size; below, the two-stage kernels (lanes = training rows)
     int opt_max_ctas = 0;
     int opt_no_fast = 0;
@@ -106,6 +108,7 @@ int launch_fused(nmma_b200_t* h, const double* pts, long long N, double* out, cu
 bool fused_has(int d, int K);
 int launch_tc(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
 int launch_tc_coeff(nmma_b200_t* h, const double* pts, long long N, double* coeff, cudaStream_t st);
+int launch_tc_coeff_parts(nmma_b200_t* h, const double* pts, long long N, float* parts, int* hsplit_out, cudaStream_t st);
 int launch_gp(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st);
 bool gp_fused_has(int d, int K);
 }  // namespace nmma

@@ -223,6 +223,30 @@ __device__ __forceinline__ double expected_mag(const DevCfg& cfg, int g, double 
     return mu;
 }
 
+// One point by one warp: `cpt` = its F*K coefficients (global or shared memory).
+__device__ __forceinline__ double backend_point(const DevCfg& cfg, const double* __restrict__ row,
+                                                const double* __restrict__ cpt, int lane) {
+    const int FK = cfg.F * cfg.K;
+    const PointScal ps = point_setup(cfg, row);
+    // sanity_check (em_likelihood.py:305-311): a filter whose light curve is all-inf, i.e.
+    // fewer than two finite magnitudes, i.e. any non-finite coefficient
+    bool ok = !ps.bad && !cfg.static_fail;
+    for (int i = lane; i < FK; i += 32) ok = ok && isfinite(cpt[i]);
+    ok = __all_sync(0xffffffffu, ok);
+    double acc = 0.0;
+    if (ok) {
+        for (int k = lane; k < cfg.nobs; k += 32) {
+            const int g = cfg.o_g[k];
+            const double t = cfg.o_t[k];
+            const double mu = expected_mag(cfg, g, t, ps, cpt);
+            const double ssys = sys_sigma(cfg, g, t, row);
+            acc += obs_term(cfg.o_m[k], mu, cfg.o_s[k], ssys, cfg.g_lim[g]);
+        }
+    }
+    acc = warp_sum(acc);
+    return (ok && isfinite(acc)) ? acc : NMMA_SENTINEL;
+}
+
 __global__ void __launch_bounds__(kBackThreads)
 backend_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, const double* __restrict__ coeff,
                     long long N, double* __restrict__ out) {
@@ -231,26 +255,35 @@ backend_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, const doub
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int FK = cfg.F * cfg.K;
     for (long long n = warp0; n < N; n += nwarps) {
-        const double* row = pts + n * cfg.P;
-        const double* cpt = coeff + (size_t)n * FK;
-        const PointScal ps = point_setup(cfg, row);
-        // sanity_check (em_likelihood.py:305-311): a filter whose light curve is all-inf, i.e.
-        // fewer than two finite magnitudes, i.e. any non-finite coefficient
-        bool ok = !ps.bad && !cfg.static_fail;
-        for (int i = lane; i < FK; i += 32) ok = ok && isfinite(cpt[i]);
-        ok = __all_sync(0xffffffffu, ok);
-        double acc = 0.0;
-        if (ok) {
-            for (int k = lane; k < cfg.nobs; k += 32) {
-                const int g = cfg.o_g[k];
-                const double t = cfg.o_t[k];
-                const double mu = expected_mag(cfg, g, t, ps, cpt);
-                const double ssys = sys_sigma(cfg, g, t, row);
-                acc += obs_term(cfg.o_m[k], mu, cfg.o_s[k], ssys, cfg.g_lim[g]);
-            }
+        const double v = backend_point(cfg, pts + n * cfg.P, coeff + (size_t)n * FK, lane);
+        if (lane == 0) out[n] = v;
+    }
+}
+
+// Latency path: the coefficients arrive as fp32 partial sums over `hsplit` hidden ranges (tensor-core kernel in coefficient
+// mode, launch_tc.cu: launch_tc_coeff_parts); added in range order in fp32 like the fused kernel's group partials, + b2,
+// then scored like backend_logl_kernel.  One warp per point, its F*K coefficients in shared memory.
+__global__ void __launch_bounds__(kBackThreads)
+backend_logl_parts_kernel(const DevCfg cfg, const double* __restrict__ pts, const float* __restrict__ parts, int hsplit,
+                          long long N, double* __restrict__ out) {
+    extern __shared__ double s_coeff[];   // [warps per block][F*K]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int K = cfg.K, FK = cfg.F * K;
+    double* cpt = s_coeff + (size_t)wib * FK;
+    for (long long n = warp0; n < N; n += nwarps) {
+        for (int i = lane; i < FK; i += 32) {
+            const int f = i / K, k = i - f * K;
+            const float* p = parts + (((size_t)n * cfg.F + f) * hsplit) * K + k;
+            float sum = 0.f;
+            for (int hs = 0; hs < hsplit; ++hs) sum += p[(size_t)hs * K];
+            cpt[i] = (double)(sum + cfg.b2[i]);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) out[n] = (ok && isfinite(acc)) ? acc : NMMA_SENTINEL;
+        __syncwarp();
+        const double v = backend_point(cfg, pts + n * cfg.P, cpt, lane);
+        if (lane == 0) out[n] = v;
+        __syncwarp();
     }
 }
 
@@ -459,114 +492,136 @@ __device__ __forceinline__ float fast_log_ndtr(float b) {
     return (q < 1e-3f) ? -q * fmaf(0.5f, q, 1.0f) : __logf(1.0f - q);
 }
 
+// Per-(point, filter) scalars of the FAST back end and the systematics-node cache of one thread.
+struct FastFilt {
+    const float2* bq;   // float2 row-pair basis pack of the filter (shared or global memory)
+    int T, lo, hi;
+    float ga, gb, dmz, dlt, dhi;
+    double z1, tsh;
+};
+struct SysCache {
+    int cur0 = -1, cur1 = -1;      // systematics nodes whose per-point values nv0 / nv1 are loaded
+    double nv0 = 0.0, nv1 = 0.0;
+};
+__device__ __forceinline__ bool fast_filt_setup(const DevCfg& cfg, int f, const PointScal& ps, const double* bp, FastFilt& ff) {
+    ff.bq = reinterpret_cast<const float2*>(bp);
+    ff.T = cfg.T; ff.lo = cfg.s_lo[f]; ff.hi = cfg.s_hi[f];
+    ff.ga = ps.ga; ff.gb = ps.gb; ff.dmz = ps.dmz;
+    ff.z1 = ps.z1; ff.tsh = ps.ts;
+    if (cfg.ext_law) {
+        const double ext = ext_mag(cfg, f, ps);
+        if (!isfinite(ext)) return false;   // the whole filter is non-finite: sanity_check fails (em_likelihood.py:305-311)
+        ff.dmz = (float)(ext + ps.dm + ps.zc);
+    }
+    ff.dlt = cfg.fast_delta; ff.dhi = 1.0f - cfg.fast_delta;
+    return true;
+}
+// One observation (record k of observed filter g, mapped directly onto the filter of `ff`) of the FAST back end.
+template <int K>
+__device__ __forceinline__ double fast_obs_term(const DevCfg& cfg, const FastFilt& ff, const float (&c)[K], int g, int k,
+                                                const double* __restrict__ row, const double* __restrict__ s_obs,
+                                                const double* __restrict__ s_samp, SysCache& syc) {
+    double out = 0.0;
+    const double* rec = s_obs + k * kObsRec;
+    const float4 rf = *reinterpret_cast<const float4*>(rec + 6);  // (float)t, (float)mag, 1/sigma, log(sigma)+C
+    const int2 cls = *reinterpret_cast<const int2*>(rec + 8);      // class, left systematics node
+    const double t = rec[0];
+    const float gq = fmaf(rf.x, ff.ga, ff.gb);
+    int j = __float2int_rd(gq);
+    const float fr = gq - (float)j;
+    bool inr = true;
+    double tj;
+    if (j >= ff.lo && j < ff.hi && fr > ff.dlt && fr < ff.dhi) {
+        tj = __dadd_rn(__dmul_rn(s_samp[j], ff.z1), ff.tsh);
+    } else {  // cold: range ends and near-node cases, settled with the exact comparisons
+        const double tlo = __dadd_rn(__dmul_rn(s_samp[ff.lo], ff.z1), ff.tsh);
+        const double thi = __dadd_rn(__dmul_rn(s_samp[ff.hi], ff.z1), ff.tsh);
+        if (!(t >= tlo && t <= thi)) {
+            inr = false;  // np.interp left = right = +inf
+            tj = 0.0; j = ff.lo;
+        } else {
+            j = locate(cfg, ff.lo, ff.hi, t, ff.z1, ff.tsh);
+            if (j >= ff.hi) j = ff.hi - 1;  // t == t_hi: weight 1 on the last interval
+            tj = __dadd_rn(__dmul_rn(s_samp[j], ff.z1), ff.tsh);
+        }
+    }
+    float mu = CUDART_INF_F;
+    if (inr) {
+        const float wgt = (float)__dsub_rn(t, tj) * ff.ga;
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const float2 v = ff.bq[i * ff.T + j];
+            d0 = fmaf(v.x, c[i], d0);
+            d1 = fmaf(v.y, c[i], d1);
+        }
+        const float2 sc = ff.bq[K * ff.T + j], mn = ff.bq[(K + 1) * ff.T + j];
+        const float a0 = fmaf(d0, sc.x, mn.x), a1 = fmaf(d1, sc.y, mn.y);
+        mu = fmaf(wgt, a1 - a0, a0) + ff.dmz;
+    }
+    bool general = cls.x == kObsGeneral;
+    if (cls.x == kObsSimple) {
+        // truncnorm.logpdf with b = +inf = the plain Gaussian log-density; mu = +inf gives -inf here where
+        // SciPy gives NaN: both end as the sentinel (core/base.py:180-181)
+        const float xq = (rf.y - mu) * rf.z;
+        out += (double)fmaf(-0.5f * xq, xq, -rf.w);
+    } else if (cls.x == kObsSampled) {
+        // sigma_sys at this observation time: the bracketing nodes and the weight are fixed per observation
+        // (systematics.py:288-291 through np.interp with 'constant' ends); the node values are per point
+        const int2 nd = *reinterpret_cast<const int2*>(rec + 9);     // right node, weight bits
+        const float2 sl = *reinterpret_cast<const float2*>(rec + 10);  // sigma_obs^2, detection limit
+        float ssys;
+        if (cls.y < 0) {
+            ssys = *reinterpret_cast<const float*>(rec + 11);          // constant budget
+        } else {
+            if (cls.y != syc.cur0 || nd.x != syc.cur1) {   // warp-uniform: all lanes walk the same observation list
+                syc.cur0 = cls.y; syc.cur1 = nd.x;
+                syc.nv0 = eval_src(cfg.sy_src[syc.cur0], row);
+                syc.nv1 = (syc.cur1 == syc.cur0) ? syc.nv0 : eval_src(cfg.sy_src[syc.cur1], row);
+            }
+            ssys = (float)fma((double)__int_as_float(nd.y), syc.nv1 - syc.nv0, syc.nv0);
+            general = !(isfinite(syc.nv0) && isfinite(syc.nv1));   // a dropped node changes the bracket: exact path
+        }
+        const float s2 = fmaf(ssys, ssys, sl.x);
+        const float inv = rsqrtf(s2);
+        const float xq = (rf.y - mu) * inv;
+        // log(s2) through MUFU.LG2 (__logf: absolute error < 4e-7 for s2 of order one) -- the libm forms of
+        // this class (logf, erfcf, log1pf) were ~300 instructions per observation and made the back end
+        // the critical path of config 3 (profiles/r02_fused_tc_c3_summary.json)
+        float term = fmaf(-0.5f * xq, xq, -0.5f * __logf(s2) - (float)NMMA_NORM_PDF_LOGC);
+        if (sl.y < CUDART_INF_F) {   // truncation at the detection limit: - log Phi((lim - mu) / sigma)
+            const float bq = (sl.y - mu) * inv;
+            term -= fast_log_ndtr(bq);
+        }
+        general = general || !(s2 > 0.f) || !(s2 < CUDART_INF_F);
+        if (!general) out += (double)term;
+    }
+    if (general) {
+        const double so = rec[2];
+        const double mud = (double)mu;
+        if (cfg.sy_mode[g] == 0 && isfinite(so)) out += obs_term_static_det(rec[1], mud, rec[3], rec[5], cfg.g_lim[g]);
+        else out += obs_term(rec[1], mud, so, sys_sigma(cfg, g, t, row), cfg.g_lim[g]);
+    }
+
+    return out;
+}
+
 template <int K, bool FAST, typename CT>
 __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, const CT (&cp)[K], const PointScal& ps,
                                                     const double* __restrict__ row, const double* __restrict__ bp,
                                                     const double* __restrict__ s_obs, const double* __restrict__ s_samp) {
-    const int lo = cfg.s_lo[f], hi = cfg.s_hi[f];
-    const double z1 = ps.z1, tsh = ps.ts;
     double lsum = 0.0;
     if constexpr (FAST) {
-        const float2* __restrict__ bq = reinterpret_cast<const float2*>(bp);
-        const int T = cfg.T;
-        const float ga = ps.ga, gb = ps.gb;
-        float dmz = ps.dmz;
-        if (cfg.ext_law) {
-            const double ext = ext_mag(cfg, f, ps);
-            if (!isfinite(ext)) return CUDART_NAN;   // the whole filter is non-finite: sanity_check fails (em_likelihood.py:305-311)
-            dmz = (float)(ext + ps.dm + ps.zc);
-        }
-        const float dlt = cfg.fast_delta, dhi = 1.0f - cfg.fast_delta;
+        FastFilt ff;
+        if (!fast_filt_setup(cfg, f, ps, bp, ff)) return CUDART_NAN;
         float c[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) c[i] = (float)cp[i];
         for (int gi = cfg.f_goff[f]; gi < cfg.f_goff[f + 1]; ++gi) {
             const int g = cfg.f_glist[gi];
             const int k1 = cfg.g_off[g + 1];
-            int cur0 = -1, cur1 = -1;      // systematics nodes whose per-point values nv0 / nv1 are loaded
-            double nv0 = 0.0, nv1 = 0.0;
-            for (int k = cfg.g_off[g]; k < k1; ++k) {
-                const double* rec = s_obs + k * kObsRec;
-                const float4 rf = *reinterpret_cast<const float4*>(rec + 6);  // (float)t, (float)mag, 1/sigma, log(sigma)+C
-                const int2 cls = *reinterpret_cast<const int2*>(rec + 8);      // class, left systematics node
-                const double t = rec[0];
-                const float gq = fmaf(rf.x, ga, gb);
-                int j = __float2int_rd(gq);
-                const float fr = gq - (float)j;
-                bool inr = true;
-                double tj;
-                if (j >= lo && j < hi && fr > dlt && fr < dhi) {
-                    tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh);
-                } else {  // cold: range ends and near-node cases, settled with the exact comparisons
-                    const double tlo = __dadd_rn(__dmul_rn(s_samp[lo], z1), tsh);
-                    const double thi = __dadd_rn(__dmul_rn(s_samp[hi], z1), tsh);
-                    if (!(t >= tlo && t <= thi)) {
-                        inr = false;  // np.interp left = right = +inf
-                        tj = 0.0; j = lo;
-                    } else {
-                        j = locate(cfg, lo, hi, t, z1, tsh);
-                        if (j >= hi) j = hi - 1;  // t == t_hi: weight 1 on the last interval
-                        tj = __dadd_rn(__dmul_rn(s_samp[j], z1), tsh);
-                    }
-                }
-                float mu = CUDART_INF_F;
-                if (inr) {
-                    const float wgt = (float)__dsub_rn(t, tj) * ga;
-                    float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-                    for (int i = 0; i < K; ++i) {
-                        const float2 v = bq[i * T + j];
-                        d0 = fmaf(v.x, c[i], d0);
-                        d1 = fmaf(v.y, c[i], d1);
-                    }
-                    const float2 sc = bq[K * T + j], mn = bq[(K + 1) * T + j];
-                    const float a0 = fmaf(d0, sc.x, mn.x), a1 = fmaf(d1, sc.y, mn.y);
-                    mu = fmaf(wgt, a1 - a0, a0) + dmz;
-                }
-                bool general = cls.x == kObsGeneral;
-                if (cls.x == kObsSimple) {
-                    // truncnorm.logpdf with b = +inf = the plain Gaussian log-density; mu = +inf gives -inf here where
-                    // SciPy gives NaN: both end as the sentinel (core/base.py:180-181)
-                    const float xq = (rf.y - mu) * rf.z;
-                    lsum += (double)fmaf(-0.5f * xq, xq, -rf.w);
-                } else if (cls.x == kObsSampled) {
-                    // sigma_sys at this observation time: the bracketing nodes and the weight are fixed per observation
-                    // (systematics.py:288-291 through np.interp with 'constant' ends); the node values are per point
-                    const int2 nd = *reinterpret_cast<const int2*>(rec + 9);     // right node, weight bits
-                    const float2 sl = *reinterpret_cast<const float2*>(rec + 10);  // sigma_obs^2, detection limit
-                    float ssys;
-                    if (cls.y < 0) {
-                        ssys = *reinterpret_cast<const float*>(rec + 11);          // constant budget
-                    } else {
-                        if (cls.y != cur0 || nd.x != cur1) {   // warp-uniform: all lanes walk the same observation list
-                            cur0 = cls.y; cur1 = nd.x;
-                            nv0 = eval_src(cfg.sy_src[cur0], row);
-                            nv1 = (cur1 == cur0) ? nv0 : eval_src(cfg.sy_src[cur1], row);
-                        }
-                        ssys = (float)fma((double)__int_as_float(nd.y), nv1 - nv0, nv0);
-                        general = !(isfinite(nv0) && isfinite(nv1));   // a dropped node changes the bracket: exact path
-                    }
-                    const float s2 = fmaf(ssys, ssys, sl.x);
-                    const float inv = rsqrtf(s2);
-                    const float xq = (rf.y - mu) * inv;
-                    // log(s2) through MUFU.LG2 (__logf: absolute error < 4e-7 for s2 of order one) -- the libm forms of
-                    // this class (logf, erfcf, log1pf) were ~300 instructions per observation and made the back end
-                    // the critical path of config 3 (profiles/r02_fused_tc_c3_summary.json)
-                    float term = fmaf(-0.5f * xq, xq, -0.5f * __logf(s2) - (float)NMMA_NORM_PDF_LOGC);
-                    if (sl.y < CUDART_INF_F) {   // truncation at the detection limit: - log Phi((lim - mu) / sigma)
-                        const float bq = (sl.y - mu) * inv;
-                        term -= fast_log_ndtr(bq);
-                    }
-                    general = general || !(s2 > 0.f) || !(s2 < CUDART_INF_F);
-                    if (!general) lsum += (double)term;
-                }
-                if (general) {
-                    const double so = rec[2];
-                    const double mud = (double)mu;
-                    if (cfg.sy_mode[g] == 0 && isfinite(so)) lsum += obs_term_static_det(rec[1], mud, rec[3], rec[5], cfg.g_lim[g]);
-                    else lsum += obs_term(rec[1], mud, so, sys_sigma(cfg, g, t, row), cfg.g_lim[g]);
-                }
-            }
+            SysCache syc;   // warp-uniform: all lanes walk the same observation list
+            for (int k = cfg.g_off[g]; k < k1; ++k) lsum += fast_obs_term<K>(cfg, ff, c, g, k, row, s_obs, s_samp, syc);
         }
     } else {
         const double ext = ext_mag(cfg, f, ps);
@@ -596,6 +651,71 @@ __device__ __forceinline__ const double* basis_src(const DevCfg& cfg, int f, int
     const size_t off = (size_t)f * cfg.T * (K + 2);
     return FAST ? reinterpret_cast<const double*>(cfg.bpack32) + off : cfg.bpack + off;
 }
+
+#ifdef NMMA_TWO_STAGE_TU
+// Latency back end, FAST instantiation (uniform single-stage grid, direct filter maps, n_coeff = K): ONE CTA PER POINT,
+// ONE THREAD PER OBSERVATION, with the fp32 per-observation term of the fused kernels (fast_obs_term); basis rows and
+// observation records come through L1 / L2.  What a one-point call pays for is the chain of dependent global loads of one
+// observation (observed filter -> model filter -> record -> basis rows, ~0.5 us per hop), so the observations must not be
+// serialised behind one another: 133 per thread in the fused kernels' back end, 5 per lane with a warp per point (31 us
+// under ncu), one here.  The coefficients arrive as fp32 partial sums over `hsplit` hidden ranges
+// (launch_tc.cu: launch_tc_coeff_parts) and are added in range order; the observation terms are added in a fixed order
+// (warp shuffles, then warp 0 over the warps' sums).
+constexpr int kLatThreads = 160;
+template <int K>
+__global__ void __launch_bounds__(kLatThreads)
+backend_logl_parts_fast_kernel(const DevCfg cfg, const double* __restrict__ pts, const float* __restrict__ parts, int hsplit,
+                               long long N, double* __restrict__ out) {
+    extern __shared__ float s_cf[];   // [F*K] coefficients, then [warps] doubles (8-byte aligned: FK rounded up to even)
+    __shared__ int s_ok;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int FK = cfg.F * K;
+    double* s_red = reinterpret_cast<double*>(s_cf + ((FK + 1) & ~1));
+    for (long long n = blockIdx.x; n < N; n += gridDim.x) {
+        const double* row = pts + n * cfg.P;
+        if (tid == 0) s_ok = 1;
+        __syncthreads();
+        for (int i = tid; i < FK; i += blockDim.x) {
+            const int f = i / K, k = i - f * K;
+            const float* p = parts + (((size_t)n * cfg.F + f) * hsplit) * K + k;
+            float sum = 0.f;
+            for (int hs = 0; hs < hsplit; ++hs) sum += p[(size_t)hs * K];
+            sum += cfg.b2[i];
+            if (!isfinite(sum)) s_ok = 0;
+            s_cf[i] = sum;
+        }
+        const PointScal ps = point_setup(cfg, row);
+        __syncthreads();
+        const bool ok = s_ok != 0 && !ps.bad && !cfg.static_fail;
+        double acc = 0.0;
+        if (ok) {
+            for (int k = tid; k < cfg.nobs; k += blockDim.x) {
+                const int g = cfg.o_g[k];
+                const int f = cfg.g_h[g * 3];          // direct maps only (checked on the host)
+                FastFilt ff;
+                if (!fast_filt_setup(cfg, f, ps, reinterpret_cast<const double*>(cfg.bpack32) + (size_t)f * cfg.T * (K + 2), ff)) {
+                    acc = CUDART_NAN;
+                    break;
+                }
+                float c[K];
+#pragma unroll
+                for (int i = 0; i < K; ++i) c[i] = s_cf[f * K + i];
+                SysCache syc;
+                acc += fast_obs_term<K>(cfg, ff, c, g, k, row, cfg.o_pack, cfg.samp, syc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < nw; ++w) tot += s_red[w];
+            out[n] = (ok && isfinite(tot)) ? tot : NMMA_SENTINEL;
+        }
+        __syncthreads();
+    }
+}
+#endif  // NMMA_TWO_STAGE_TU
 
 // FAST = sample grid is the (uniform) training grid itself: stage 1 is the identity and the
 // interval search starts from an O(1) guess.

@@ -16,16 +16,25 @@ __global__ void combine_parts_kernel(const double* __restrict__ parts, int fspli
     out[n] = isfinite(s) ? s : NMMA_SENTINEL;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel function, not to the handle or the launcher: one
+// high-water mark per instantiation (two launchers with their own marks lowered each other's setting), and one driver
+// call per configuration instead of one per launch (one-point latency).
+template <int K, bool FAST, bool SPLIT, bool COEFF>
+int ensure_tc_smem(nmma_b200_t* h, size_t smem) {
+    static size_t mark = 0;
+    if (mark < smem) {
+        CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, FAST, SPLIT, COEFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mark = smem;
+    }
+    return NMMA_B200_OK;
+}
+
 template <bool FAST>
 int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
     constexpr int K = 10;
     const size_t smem = tc_smem_bytes(K, h->T, h->cfg.S, h->cfg.nobs);
-    static size_t attr_smem[2] = {0, 0};   // per instantiation (FAST): the attribute is per function, not per handle
-    if (attr_smem[FAST] < smem) {          // one driver call per configuration instead of two per launch (one-point latency)
-        CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, FAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, FAST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem[FAST] = smem;
-    }
+    if (int rc = ensure_tc_smem<K, FAST, true, false>(h, smem)) return rc;
+    if (int rc = ensure_tc_smem<K, FAST, false, false>(h, smem)) return rc;
     const long long super = (long long)kTcTile * kTcTiles;
     const long long nsuper = (N + super - 1) / super;
     long long grid = h->sm_count;  // one CTA per SM: each CTA owns all 512 TMEM columns of its SM
@@ -46,8 +55,8 @@ int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cud
         dst = h->tc_parts;
     }
     grid = std::max<long long>(1, std::min(grid, nsuper * fsplit));
-    if (fsplit > 1) fused_tc_logl_kernel<K, FAST, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, dst, fsplit);
-    else fused_tc_logl_kernel<K, FAST, false><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, dst, 1);
+    if (fsplit > 1) fused_tc_logl_kernel<K, FAST, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, dst, fsplit, 1);
+    else fused_tc_logl_kernel<K, FAST, false><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, dst, 1, 1);
     CU(cudaGetLastError());
     if (fsplit > 1) {
         combine_parts_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h->tc_parts, fsplit, N, out);
@@ -64,12 +73,8 @@ int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cud
 int launch_tc_coeff(nmma_b200_t* h, const double* pts, long long N, double* coeff, cudaStream_t st) {
     constexpr int K = kTcN2;
     const size_t smem = tc_smem_bytes(K, h->T, h->cfg.S, h->cfg.nobs);
-    static size_t attr_smem = 0;
-    if (attr_smem < smem) {
-        CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(fused_tc_logl_kernel<K, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    if (int rc = ensure_tc_smem<K, false, true, true>(h, smem)) return rc;
+    if (int rc = ensure_tc_smem<K, false, false, true>(h, smem)) return rc;
     const long long super = (long long)kTcTile * kTcTiles;
     const long long nsuper = (N + super - 1) / super;
     long long grid = h->sm_count;
@@ -77,11 +82,35 @@ int launch_tc_coeff(nmma_b200_t* h, const double* pts, long long N, double* coef
     int fsplit = 1;   // small batches: the filters of a super-tile over several CTAs (each part writes its own filters)
     if (!h->opt_no_fsplit && nsuper * 2 <= grid) fsplit = (int)std::min<long long>(h->F, grid / nsuper);
     grid = std::max<long long>(1, std::min(grid, nsuper * fsplit));
-    if (fsplit > 1) fused_tc_logl_kernel<K, false, true, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, fsplit);
-    else fused_tc_logl_kernel<K, false, false, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, 1);
+    if (fsplit > 1) fused_tc_logl_kernel<K, false, true, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, fsplit, 1);
+    else fused_tc_logl_kernel<K, false, false, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, 1, 1);
     CU(cudaGetLastError());
     h->launches += 1;
     h->last_ctas_per_sm = 1;
+    return NMMA_B200_OK;
+}
+
+// Latency path (one point per call from bilby / pymultinest, small live-point batches): the filters AND the hidden layer of
+// each 256-point super-tile are spread over the SMs; `parts` receives fp32 partial coefficient sums
+// [N][F][hsplit][K] that backend_logl_parts_kernel (api.cu) adds in range order.  Returns hsplit through *hsplit_out.
+int launch_tc_coeff_parts(nmma_b200_t* h, const double* pts, long long N, float* parts, int* hsplit_out, cudaStream_t st) {
+    constexpr int K = kTcN2;
+    const size_t smem = tc_smem_bytes(K, h->T, h->cfg.S, h->cfg.nobs);
+    if (int rc = ensure_tc_smem<K, false, true, true>(h, smem)) return rc;
+    const long long super = (long long)kTcTile * kTcTiles;
+    const long long nsuper = (N + super - 1) / super;
+    const long long grid_max = h->opt_max_ctas > 0 ? std::min<long long>(h->sm_count, h->opt_max_ctas) : h->sm_count;
+    const int fsplit = (int)std::max<long long>(1, std::min<long long>(h->F, grid_max / nsuper));
+    // hidden ranges: a power of two that leaves every range an even number of chunks (two TMEM buffers per tile)
+    int hsplit = 1;
+    while (nsuper * fsplit * (hsplit * 2) <= grid_max && h->cfg.tc_nch % (hsplit * 4) == 0) hsplit *= 2;
+    const long long grid = std::max<long long>(1, std::min(grid_max, nsuper * fsplit * hsplit));
+    fused_tc_logl_kernel<K, false, true, true><<<(unsigned)grid, kTcThreads, smem, st>>>(
+        h->cfg, pts, N, reinterpret_cast<double*>(parts), fsplit, hsplit);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->last_ctas_per_sm = 1;
+    *hsplit_out = hsplit;
     return NMMA_B200_OK;
 }
 

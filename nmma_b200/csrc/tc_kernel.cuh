@@ -225,8 +225,14 @@ struct TcBars {
 // width kTcN2 and cfg.K the real one.
 template <int K, bool FAST, bool SPLIT, bool COEFF = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
-fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ out, int fsplit_arg) {
+fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ out, int fsplit_arg,
+                     int hsplit_arg) {
     const int fsplit = SPLIT ? fsplit_arg : 1;   // SPLIT = false: the throughput instantiation, index arithmetic folds away
+    // COEFF + SPLIT only (one-point / small-batch latency, launch_tc.cu: launch_tc_coeff_parts): the hidden layer of a
+    // filter is cut into hsplit chunk ranges as well, each CTA hands out the PARTIAL coefficient sums of its range as fp32
+    // [N][F][hsplit][cfg.K] (no b2), and backend_logl_parts_kernel adds them in range order before it scores them
+    const int hsplit = (SPLIT && COEFF) ? hsplit_arg : 1;
+    const int nparts = fsplit * hsplit;
     // Work item = (256-point super-tile, filter part): with fsplit > 1 (small batches, launch_tc.cu) the filters of one
     // super-tile are spread over fsplit CTAs and `out` receives the per-part sums [N][fsplit] (NaN = failed) that
     // combine_parts_kernel adds in a fixed order; with fsplit == 1 `out` is the final log-likelihood.
@@ -245,14 +251,15 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
     TcBars* bars = reinterpret_cast<TcBars*>(smem + wbytes + 2 * bslot + obytes + sbytes + tc_cbuf_bytes());
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int F = cfg.F, NCH = cfg.tc_nch;
+    const int F = cfg.F, NCHT = cfg.tc_nch, NCH = NCHT / hsplit;   // chunks per filter, per (filter, hidden range)
     const int Kr = COEFF ? cfg.K : K;   // real n_coeff
     constexpr int SUPER = kTcTile * kTcTiles;
-    const long long nsuper = ((N + SUPER - 1) / SUPER) * fsplit;   // work items
+    const long long nsuper = ((N + SUPER - 1) / SUPER) * nparts;   // work items
     const long long my_super = (nsuper > blockIdx.x) ? (nsuper - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     // filters [f0, f1) of work item w: part p = w % fsplit takes p F / fsplit .. (p + 1) F / fsplit
-#define TC_PART_F0(w) (SPLIT ? (int)(((w) % fsplit) * F / fsplit) : 0)
-#define TC_PART_F1(w) (SPLIT ? (int)(((w) % fsplit + 1) * F / fsplit) : F)
+#define TC_PART_F0(w) (SPLIT ? (int)(((w) % nparts / hsplit) * F / fsplit) : 0)
+#define TC_PART_F1(w) (SPLIT ? (int)(((w) % nparts / hsplit + 1) * F / fsplit) : F)
+#define TC_PART_HS(w) ((SPLIT && COEFF) ? (int)((w) % nparts % hsplit) : 0)
     const uint32_t half = (uint32_t)NCH >> 1;  // NCH is even: TMEM buffer = c & 1, its use count = vseq * half + (c >> 1)
 
     if (tid == 0) {
@@ -273,8 +280,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         mbar_fence_init();
     }
     if (warp == 11) tmem_alloc(&bars->tmem_base, 512);
-    for (int i = tid; i < cfg.nobs * kObsRec; i += kTcThreads) s_obs[i] = cfg.o_pack[i];
-    for (int i = tid; i < cfg.S; i += kTcThreads) s_samp[i] = cfg.samp[i];
+    if constexpr (!COEFF) {   // the coefficient mode has no back end: nothing to stage
+        for (int i = tid; i < cfg.nobs * kObsRec; i += kTcThreads) s_obs[i] = cfg.o_pack[i];
+        for (int i = tid; i < cfg.S; i += kTcThreads) s_samp[i] = cfg.samp[i];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -290,7 +299,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         uint32_t vseq = 0;  // (super-tile, filter) sequence number of this CTA
         for (long long it = 0; it < my_super; ++it) {
             const long long item = blockIdx.x + it * gridDim.x;
-            const long long n = (item / fsplit) * SUPER + (long long)t * kTcTile + pidx;
+            const long long n = (item / nparts) * SUPER + (long long)t * kTcTile + pidx;
             const double* row = pts + (n < N ? n : 0) * cfg.P;
             for (int f = TC_PART_F0(item), f1 = TC_PART_F1(item); f < f1; ++f, ++vseq) {
                 // ---- layer-1 A operand: [x_hi, 1, 0.. | x_lo, 0, 0..] (fp64 scaling, fp32 cast like Keras) ----
@@ -399,7 +408,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
 #pragma unroll
                 for (int k = 0; k < K; ++k)
-                    if (!COEFF || k < Kr) cb[k * kTcTile] = okx ? acc[k] + cfg.b2[f * Kr + k] : CUDART_NAN_F;
+                    if (!COEFF || k < Kr) cb[k * kTcTile] = okx ? acc[k] + (hsplit > 1 ? 0.f : cfg.b2[f * Kr + k]) : CUDART_NAN_F;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->c_full[t][slot]);
             }
@@ -504,7 +513,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 }
                 __syncwarp();
             }
-            const float* src = cfg.tcpack + (size_t)f * NCH * kTcChunkFloats;
+            const float* src = cfg.tcpack + ((size_t)f * NCHT + (size_t)TC_PART_HS(item) * NCH) * kTcChunkFloats;
             for (int c = 0; c < NCH; ++c) {
                 TC_WAIT_PROD(&bars->w_free[st], ph ^ 1);
                 if (elect_one()) {
@@ -533,7 +542,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         uint32_t vseq = 0;
         for (long long it = 0; it < my_super; ++it) {
             const long long item = blockIdx.x + it * gridDim.x;
-            const long long n = (item / fsplit) * SUPER + (long long)t * kTcTile + pidx;
+            const long long n = (item / nparts) * SUPER + (long long)t * kTcTile + pidx;
             const bool live = n < N;
             const double* row = pts + (live ? n : 0) * cfg.P;
             if constexpr (COEFF) {
@@ -541,7 +550,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     const int slot = (int)(vseq & 1);
                     TC_WAIT_BACK(&bars->c_full[t][slot], (vseq >> 1) & 1);
                     const float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
-                    if (live) {
+                    if (live && hsplit > 1) {
+                        float* dst = reinterpret_cast<float*>(out) + (((size_t)n * F + f) * hsplit + TC_PART_HS(item)) * Kr;
+                        for (int k = 0; k < Kr; ++k) dst[k] = cb[k * kTcTile];
+                    } else if (live) {
                         double* dst = out + ((size_t)n * F + f) * Kr;
                         for (int k = 0; k < Kr; ++k) dst[k] = (double)cb[k * kTcTile];
                     }
@@ -623,6 +635,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
     if (warp == 11) tmem_dealloc(tmem, 512);
 #undef TC_PART_F0
 #undef TC_PART_F1
+#undef TC_PART_HS
 }
 
 }  // namespace nmma

@@ -367,6 +367,106 @@ class SVDLightCurveModel(LightCurveModelContainer):
         return self.generate_lightcurve(sample_times, parameters, filters=wavelengths)
 
 
+class CombinedLightCurveModelContainer:
+    """``nmma/em/model.py:1342-1510``: several light-curve models evaluated on the same parameters, their light curves added
+    in flux (``stack_magnitudes``: -2.5 log10 sum 10^(-0.4 m), through logsumexp like the reference).
+
+    Host-side composition: each sub-model (an :class:`SVDLightCurveModel`) evaluates its magnitudes on the GPU, the stack is
+    a handful of vector operations per call.  That serves ``generate_lightcurve`` / ``gen_detector_lc`` (best-fit plots,
+    injections).  The batched likelihood needs the flux sum on the device before the interpolation to the observation
+    times and is not implemented for combined models: ``EMTransientLikelihood`` raises for them."""
+
+    def __init__(self, models, model_args=None):
+        from . import utils
+        self.lc_models = list(models) if model_args is None else [m(*model_args[i]) for i, m in enumerate(models)]
+        self.model = [m.model for m in self.lc_models]
+        self.all_filters = set().union(*[m.filters for m in self.lc_models])
+        self.filters = sorted(self.all_filters)
+        self.compatible_filters, _ = utils.get_filter_name_mapping(self.all_filters, extra_known=tuple(self.all_filters))
+        self.model_times = np.array(sorted(set().union(*[np.asarray(m.model_times, float).tolist() for m in self.lc_models])))
+        self.model_parameters = [k for m in self.lc_models for k in m.model_parameters]
+
+    def __repr__(self):
+        return "Combination of " + " and ".join(repr(m) for m in self.lc_models)
+
+    def check_vs_priors(self, priors):
+        for m in self.lc_models:
+            m.check_vs_priors(priors)
+
+    @property
+    def citation(self):
+        out = {}
+        for m in self.lc_models:
+            out.update(m.citation)
+        return out
+
+    @property
+    def good_parameters(self):
+        return bool(np.prod([getattr(m, "good_parameters", True) for m in self.lc_models]))
+
+    def parameter_conversion(self, parameters):
+        for m in self.lc_models:
+            parameters = m.parameter_conversion(parameters)
+        return parameters
+
+    def new_engine(self):
+        raise NotImplementedError("combined light-curve models have no device engine: the batched likelihood covers single "
+                                  "SVD surrogates (generate_lightcurve / gen_detector_lc of the combination are available)")
+
+    def stack_magnitudes(self, mags_per_model):
+        """``:1486-1510``: per filter, the flux sum of the models that provide it (directly or as a filter average)."""
+        from scipy.special import logsumexp
+        from . import utils
+        ln10 = np.log(10.0)
+        stacked = {}
+        for filt in self.all_filters:
+            terms = []
+            for mag in mags_per_model:
+                try:
+                    m = mag[self.compatible_filters[filt]]
+                except KeyError:
+                    try:
+                        m = utils.average_mags(mag, filt)
+                    except (ValueError, KeyError):
+                        continue
+                terms.append(-2.0 / 5.0 * ln10 * np.asarray(m, float))
+            if not terms:
+                stacked[filt] = np.full_like(self.model_times, np.inf)
+            else:
+                stacked[filt] = -5.0 / 2.0 * logsumexp(terms, axis=0) / ln10
+        return stacked
+
+    def generate_lightcurve(self, sample_times, parameters, return_all=False):
+        per_model = []
+        for m in self.lc_models:
+            lc = m.generate_lightcurve(sample_times, parameters)
+            if not lc:
+                return lc
+            per_model.append(lc)
+        return per_model if return_all else self.stack_magnitudes(per_model)
+
+    def gen_detector_lc(self, parameters, sample_times=None, return_all=False):
+        """``:1410-1460``: every model in its own detector frame, brought onto the union of the time grids
+        (``autocomplete_data`` with +inf outside a model's range), then stacked."""
+        from . import utils
+        lcs, times = [], []
+        for m in self.lc_models:
+            t, lc = m.gen_detector_lc(parameters, sample_times)
+            if not lc:
+                return t, lc
+            lcs.append(lc)
+            times.append(np.asarray(t, float))
+        if return_all:
+            return times, lcs
+        joint = np.array(sorted(set().union(*[t.tolist() for t in times]))) if sample_times is None else times[-1]
+        on_joint = [{f: utils.autocomplete_data(joint, t, v, extrapolate=np.inf) for f, v in lc.items()}
+                    for t, lc in zip(times, lcs)]
+        return joint, self.stack_magnitudes(on_joint)
+
+
+GenericCombineLightCurveModel = CombinedLightCurveModelContainer   # the reference's legacy synonym (``:1513``)
+
+
 def create_light_curve_model_from_args(model_name_arg, args, filters=None, sample_times=None):
     """``nmma/em/model.py:1617-1658`` restricted to SVD kilonova models."""
     from .utils import setup_sample_times
@@ -376,12 +476,15 @@ def create_light_curve_model_from_args(model_name_arg, args, filters=None, sampl
     if sample_times is None:
         sample_times = setup_sample_times(args)
     names = model_name_arg.split(",") if isinstance(model_name_arg, str) else list(model_name_arg)
-    if len(names) != 1:
-        raise NotImplementedError("combined light-curve models are outside the nmma_b200 hot path")
-    return SVDLightCurveModel(
-        names[0], svd_path=getattr(args, "svd_path", None),
-        extinction_law=getattr(args, "em_extinction_law", None),
-        svd_mag_ncoeff=getattr(args, "svd_mag_ncoeff", None),
-        svd_lbol_ncoeff=getattr(args, "svd_lbol_ncoeff", None),
-        interpolation_type=getattr(args, "interpolation_type", "keras"),
-        filters=filters, sample_times=sample_times, local_only=getattr(args, "local_only", True))
+    def one(name):
+        return SVDLightCurveModel(
+            name, svd_path=getattr(args, "svd_path", None),
+            extinction_law=getattr(args, "em_extinction_law", None),
+            svd_mag_ncoeff=getattr(args, "svd_mag_ncoeff", None),
+            svd_lbol_ncoeff=getattr(args, "svd_lbol_ncoeff", None),
+            interpolation_type=getattr(args, "interpolation_type", "keras"),
+            filters=filters, sample_times=sample_times, local_only=getattr(args, "local_only", True))
+
+    if len(names) != 1:       # SVD surrogates only (afterglowpy / analytic models are outside the path)
+        return CombinedLightCurveModelContainer([one(n) for n in names])
+    return one(names[0])

@@ -47,6 +47,9 @@ def _paths(lik, pts, cols):
         eng.set_option("no_fast_backend", 1)
         out["fused_tc_generic"] = eng.logl_host(pts)
         eng.set_option("no_fast_backend", 0)
+    if eng.get_info("tc_front_supported"):
+        eng.set_option("path", 5)                             # latency path: filters and hidden ranges over all SMs + back end
+        out["latency_hsplit"] = eng.logl_host(pts)
     if eng.get_info("gp_fused_supported"):
         eng.set_option("path", 4)                             # fused GP kernel (thread = point, item = (tile, filter))
         out["fused_gp"] = eng.logl_host(pts)

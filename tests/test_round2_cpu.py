@@ -2,6 +2,7 @@
 the effective-wavelength table, Constraint / Ebv layouts, and the prior construction of ``create_prior_from_args``."""
 import json
 import os
+import sys
 from types import SimpleNamespace
 
 import numpy as np
@@ -238,3 +239,57 @@ def test_fast_log_ndtr_restatement():
     got = np.where(b > 0, np.where(b > 8.3, 0.0, pos), lg)
     ref = log_ndtr(b.astype(np.float64))
     assert (np.abs(got - ref) / np.maximum(1.0, np.abs(ref))).max() < 6e-7
+
+
+class _StubModel:
+    """Minimal LightCurveModel for the combined-container tests: constant magnitudes per filter on its own time grid."""
+
+    def __init__(self, name, filters, times, offset):
+        self.model, self.filters, self.model_times, self.model_parameters = name, list(filters), np.asarray(times, float), ["a"]
+        self.offset, self.citation, self.good_parameters = offset, {name: "cite"}, True
+
+    def parameter_conversion(self, p):
+        return p
+
+    def check_vs_priors(self, p):
+        pass
+
+    def generate_lightcurve(self, t, p):
+        return {f: 20.0 + self.offset + 0.1 * i + 0.05 * np.asarray(t, float) for i, f in enumerate(self.filters)}
+
+    def gen_detector_lc(self, p, sample_times=None):
+        t = self.model_times * 1.01 + self.offset
+        return t, {f: 20.0 + self.offset + 0.1 * i + 0.05 * t for i, f in enumerate(self.filters)}
+
+
+def test_combined_model_container_stacks_fluxes():
+    """CombinedLightCurveModelContainer (nmma/em/model.py:1342-1510): flux sum per filter, union time grid, +inf outside a
+    sub-model's range; compared with the reference's own class when /root/reference is available (this container)."""
+    from nmma_b200.em import CombinedLightCurveModelContainer
+    a = _StubModel("A", ["ps1::g", "ps1::r"], np.linspace(0, 10, 5), 0.0)
+    b = _StubModel("B", ["ps1::r", "sdssu"], np.linspace(0, 8, 4), 1.0)
+    comb = CombinedLightCurveModelContainer([a, b])
+    t = np.linspace(0, 5, 4)
+    lc = comb.generate_lightcurve(t, {"a": 1.0})
+    ma, mb = a.generate_lightcurve(t, {})["ps1::r"], b.generate_lightcurve(t, {})["ps1::r"]
+    assert np.allclose(lc["ps1::r"], -2.5 * np.log10(10 ** (-0.4 * ma) + 10 ** (-0.4 * mb)), rtol=0, atol=1e-12)
+    assert np.allclose(lc["ps1::g"], a.generate_lightcurve(t, {})["ps1::g"], rtol=0, atol=1e-12) and set(lc) == {"ps1::g", "ps1::r", "sdssu"}
+    tj, lcj = comb.gen_detector_lc({"a": 1.0})
+    assert np.array_equal(tj, np.array(sorted(set((a.model_times * 1.01).tolist()) | set((b.model_times * 1.01 + 1.0).tolist()))))
+    assert lcj["ps1::r"][0] == pytest.approx(20.1, abs=1e-12)                       # t = 0: model B has not started (+inf -> no flux)
+    assert comb.model_parameters == ["a", "a"] and comb.good_parameters
+    with pytest.raises(NotImplementedError):
+        comb.new_engine()                                               # no device engine: the batched likelihood is single-model
+    if not os.path.isdir("/root/reference/nmma"):
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import reference_stubs as RS
+    ref_cls = RS.load_reference()["model"].CombinedLightCurveModelContainer
+    rc = ref_cls([a, b])
+    rlc = rc.generate_lightcurve(t, {"a": 1.0})
+    for f in lc:
+        assert np.array_equal(lc[f], rlc[f]), f
+    rt, rlcj = rc.gen_detector_lc({"a": 1.0})
+    assert np.array_equal(rt, tj)
+    for f in lcj:
+        assert np.array_equal(lcj[f], rlcj[f]), f

@@ -25,10 +25,10 @@ for n in (1, 16, 256, 1024, 4096):
 eng = lik.sub_model.engine_for(cols)
 big, _ = wl["priors"].sample_array(262144, np.random.default_rng(4), cols)
 bigd = torch.from_numpy(big).cuda()
-print("device-resident, us per call by path (1 = fused FFMA, 2 = two-stage, 3 = tensor core):")
-for n in (64, 256, 1024, 4096, 16384, 65536, 262144):
+print("device-resident, us per call by path (1 = fused FFMA, 2 = two-stage, 3 = tensor core, 5 = hidden-split tensor core + back end):")
+for n in (1, 64, 256, 512, 1024, 2048, 4096, 16384, 65536, 262144):
     row = []
-    for path in (1, 2, 3):
+    for path in (1, 2, 3, 5):
         eng.set_option("path", path)
         x = bigd[:n].contiguous(); out = torch.empty(n, dtype=torch.float64, device="cuda")
         try:
