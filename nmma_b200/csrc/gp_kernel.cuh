@@ -27,8 +27,10 @@
 // (tools/fp64_rate.cu: "DFMA3r"), and the ~20 integer / load instructions per value cost almost a full slot each next to
 // the fp64 stream; 8, 12, 16 or 20 warps per SM and 2- or 10-way interleaving all land within 5 % of each other.  The
 // per-pair constants cannot be moved off the register file: ptxas loads constant-bank / kernel-parameter operands into
-// vector registers inside the loop (tried: parameter struct indexed by a uniform filter index, and 16 loop instances
-// with compile-time offsets: 20.9 and 19.3 M evals/s).
+// vector registers inside the loop (tried: parameter struct indexed by a uniform filter index, 16 loop instances with
+// compile-time offsets, and the polynomial coefficients in __constant__ memory: 20.9, 19.3 and 20.0 M evals/s -- every
+// constant that lands in a vector register turns a 2-operand DFMA into a 3-operand one; 128-bit loads of the alphas:
+// 20.8 M, the kernel sits at the 128-register limit and ten more live registers spill).
 // gf_pow is restated operation by operation in tests/test_rq_pow.py (accuracy vs a 40-digit reference).
 #pragma once
 #include "kernels.cuh"
