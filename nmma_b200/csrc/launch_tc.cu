@@ -82,8 +82,8 @@ int launch_tc_coeff(nmma_b200_t* h, const double* pts, long long N, double* coef
     int fsplit = 1;   // small batches: the filters of a super-tile over several CTAs (each part writes its own filters)
     if (!h->opt_no_fsplit && nsuper * 2 <= grid) fsplit = (int)std::min<long long>(h->F, grid / nsuper);
     grid = std::max<long long>(1, std::min(grid, nsuper * fsplit));
-    if (fsplit > 1) fused_tc_logl_kernel<K, false, true, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, fsplit, 1);
-    else fused_tc_logl_kernel<K, false, false, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, 1, 1);
+    if (fsplit > 1) fused_tc_logl_kernel<K, false, true, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, fsplit, 0);
+    else fused_tc_logl_kernel<K, false, false, true><<<(unsigned)grid, kTcThreads, smem, st>>>(h->cfg, pts, N, coeff, 1, 0);
     CU(cudaGetLastError());
     h->launches += 1;
     h->last_ctas_per_sm = 1;

@@ -231,7 +231,8 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
     // COEFF + SPLIT only (one-point / small-batch latency, launch_tc.cu: launch_tc_coeff_parts): the hidden layer of a
     // filter is cut into hsplit chunk ranges as well, each CTA hands out the PARTIAL coefficient sums of its range as fp32
     // [N][F][hsplit][cfg.K] (no b2), and backend_logl_parts_kernel adds them in range order before it scores them
-    const int hsplit = (SPLIT && COEFF) ? hsplit_arg : 1;
+    const bool parts_mode = SPLIT && COEFF && hsplit_arg > 0;   // hsplit_arg = 0: plain coefficient mode (fp64, + b2)
+    const int hsplit = parts_mode ? hsplit_arg : 1;
     const int nparts = fsplit * hsplit;
     // Work item = (256-point super-tile, filter part): with fsplit > 1 (small batches, launch_tc.cu) the filters of one
     // super-tile are spread over fsplit CTAs and `out` receives the per-part sums [N][fsplit] (NaN = failed) that
@@ -408,7 +409,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
 #pragma unroll
                 for (int k = 0; k < K; ++k)
-                    if (!COEFF || k < Kr) cb[k * kTcTile] = okx ? acc[k] + (hsplit > 1 ? 0.f : cfg.b2[f * Kr + k]) : CUDART_NAN_F;
+                    if (!COEFF || k < Kr) cb[k * kTcTile] = okx ? acc[k] + (parts_mode ? 0.f : cfg.b2[f * Kr + k]) : CUDART_NAN_F;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->c_full[t][slot]);
             }
@@ -550,7 +551,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     const int slot = (int)(vseq & 1);
                     TC_WAIT_BACK(&bars->c_full[t][slot], (vseq >> 1) & 1);
                     const float* cb = s_c + ((size_t)(t * 2 + slot) * kTcN2) * kTcTile + pidx;
-                    if (live && hsplit > 1) {
+                    if (live && parts_mode) {
                         float* dst = reinterpret_cast<float*>(out) + (((size_t)n * F + f) * hsplit + TC_PART_HS(item)) * Kr;
                         for (int k = 0; k < Kr; ++k) dst[k] = cb[k * kTcTile];
                     } else if (live) {
