@@ -36,7 +36,7 @@ def _all_paths(eng, pts):
     return out
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(24))
 def test_random_configuration(seed):
     import torch
     assert torch.cuda.is_available()
@@ -72,9 +72,26 @@ def test_random_configuration(seed):
     if rng.random() < 0.4:
         key = "log10_vej" if kind == "gp" else "KNphi"
         priors[key] = float(rng.uniform(priors[key].minimum, priors[key].maximum))      # a fixed model parameter
+    extras = []
+    if rng.random() < 0.3:                              # redshift sampled independently of the distance (em/model.py:288-303)
+        priors["redshift"] = Uniform(0.0, 0.08, name="redshift")
+        extras.append("z")
+    if kind == "mlp" and rng.random() < 0.3:            # a Constraint on a derived key (core/base.py:67-68)
+        from nmma_b200.core.priors import Constraint
+        priors["KNtheta"] = Constraint(minimum=10.0, maximum=80.0, name="KNtheta")
+        extras.append("constraint")
+    law, coef = None, None
+    if rng.random() < 0.35:                             # dust: Ebv sampled, P92 SMC in the host frame or a linear law
+        from types import SimpleNamespace
+        from nmma_b200.em.prior import extinction_prior
+        priors = extinction_prior(priors, SimpleNamespace(use_Ebv=True, Ebv_max=0.5724))
+        law = str(rng.choice(["P92_SMC_host", "G23_MW"]))
+        if law == "G23_MW":
+            coef = {f: float(rng.uniform(0.3, 4.5)) for f in filters}
+        extras.append(law)
     lik, olik, fixed, cols = build_pair(core, name, filters, obs_filters, lc_data, priors, kind=kind,
                                         sample_times=sample_times, error_budget=float(rng.uniform(0.3, 1.2)),
-                                        systematics=yaml, detection_limit=limit)
+                                        systematics=yaml, detection_limit=limit, extinction_law=law, extinction_coef=coef)
     n = int(rng.choice([1, 37, 300, 1500, 5000])) if kind == "mlp" else int(rng.choice([5, 200, 4500]))
     pts, _ = priors.sample_array(n, np.random.default_rng(seed), cols)
     if n > 20:
@@ -85,7 +102,7 @@ def test_random_configuration(seed):
     eng = lik.sub_model.engine_for(cols)
     results = _all_paths(eng, pts)
     tag = (f"seed {seed}: {kind} K={K} F={nf} obs={sum(counts[f] for f in obs_filters)} grid={grid_kind} sys={sysk} "
-           f"limit={'inf' if limit is np.inf else 'finite'} N={n} auto path {eng.get_info('last_path')}")
+           f"limit={'inf' if limit is np.inf else 'finite'} {'+'.join(extras)} N={n} auto path {eng.get_info('last_path')}")
     for k, v in results.items():                        # diagnostics first: where the worst disagreement sits
         d = np.abs(v[:n_ref] - ref) / np.maximum(1.0, np.abs(ref))
         d[(v[:n_ref] == SENTINEL) | (ref == SENTINEL)] = 0.0
@@ -98,3 +115,32 @@ def test_random_configuration(seed):
     for k, v in results.items():                        # beyond the oracle sample: every path against the two-stage kernels
         assert np.array_equal(v == SENTINEL, base == SENTINEL), (tag, k)
         assert_logl_close(v, base)
+
+
+def test_batch_size_sequence_on_one_engine():
+    """One handle, batches of very different sizes back to back: every automatic path in turn, growing and shrinking
+    scratch buffers (coefficients, partial sums, GP tickets), results independent of what ran before."""
+    import torch
+    assert torch.cuda.is_available()
+    from nmma_b200 import synthetic as syn
+    for kind, name, sizes in (("mlp", "Bu2019lm", [1, 5000, 37, 300, 70000, 2, 1500, 1024, 1025]),
+                              ("gp", "Ka2017", [3, 6000, 200, 4096, 4095, 9000, 1])):
+        filters = ["ps1::g", "ps1::r", "2massks", "sdssu"]
+        core = syn.random_model(name, filters, kind=kind, seed=3, **({"Ntr": 120} if kind == "gp" else {}))
+        rng = np.random.default_rng(5)
+        lc_data = synthetic_observations(filters, rng, n_per_filter=9, tmax=12.0, n_ul=1, mag0=18.0, slope=0.2)
+        priors = syn.ka2017_prior() if kind == "gp" else syn.bu2019lm_prior()
+        lik, _, _, cols = build_pair(core, name, filters, filters, lc_data, priors, kind=kind)
+        eng = lik.sub_model.engine_for(cols)
+        big, _ = priors.sample_array(max(sizes), np.random.default_rng(9), cols)
+        eng.set_option("path", 2)
+        base = eng.logl_host(big[:6000])                 # plain two-stage kernels
+        eng.set_option("path", 0)
+        seen = set()
+        for n in sizes + sizes[::-1]:
+            got = eng.logl_host(big[:n])
+            seen.add(eng.get_info("last_path"))
+            m = min(n, 6000)
+            assert_logl_close(got[:m], base[:m])
+        print(kind, "automatic paths seen", sorted(seen))
+        assert seen >= ({5, 3} if kind == "mlp" else {2, 4})
