@@ -97,7 +97,10 @@ int launch_frontend(nmma_b200_t* h, const double* pts, long long N, double* coef
         const size_t smem = (size_t)kGpPts * h->Ntr * sizeof(double);
         CU(cudaFuncSetAttribute(coeff_gp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ntiles, (long long)h->sm_count * 8));
-        coeff_gp_kernel<<<grid, kGpThreads, smem, st>>>(h->cfg, pts, N, coeff);
+        // few tiles: spread the F K (filter, coefficient) pairs of each over several CTAs, one pair per warp at most
+        const long long pair_groups = ((long long)h->F * h->K + kGpThreads / 32 - 1) / (kGpThreads / 32);
+        const unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>(pair_groups, (long long)h->sm_count * 4 / std::max<long long>(1, ntiles)));
+        coeff_gp_kernel<<<dim3(grid, gy), kGpThreads, smem, st>>>(h->cfg, pts, N, coeff);
     }
     CU(cudaGetLastError());
     h->launches += 1;
@@ -312,6 +315,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
     h->fused_supported = false;
     h->tc_supported = false;
     h->gp_fused_supported = false;
+    h->fast_backend_ok = false;
     // coefficient mode of the tensor-core kernel: no observations needed (generate_lightcurve / coeffs use it too)
     if (!h->have_obs) { c.G = 0; c.nobs = 0; }
     h->tc_front_supported = (h->kind == 0) && K <= kTcN2 && c.tc_nch > 0 &&
@@ -413,6 +417,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         if (int rc = upload(h, sy_t, &c.sy_t)) return rc;
         if (int rc = upload(h, f_goff, &c.f_goff)) return rc;
         if (int rc = upload(h, f_glist, &c.f_glist)) return rc;
+        h->fast_backend_ok = direct && c.single_stage && c.uniform;   // what fused_filter_logl<FAST> / fast_obs_term assume
         h->fused_supported = (h->kind == 0) && direct && fused_has(d, K) &&
                              fused_smem_bytes(d, K, T, c.S, nobs) <= 227 * 1024;
         h->tc_supported = (h->kind == 0) && direct && K == 10 && c.tc_nch > 0 &&
@@ -727,7 +732,7 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((N + wpb - 1) / wpb, (long long)h->sm_count * 16));
         // FAST per-observation terms (lanes over observations) where the fused kernels would use them too; else generic fp64
         const bool fast = h->tc_supported && h->cfg.single_stage && h->cfg.uniform && !h->opt_no_fast;
-        if (fast) backend_logl_parts_fast_kernel<10><<<(unsigned)std::min<long long>(N, (long long)h->sm_count * 8), kLatThreads,
+        if (fast) backend_logl_parts_fast_kernel<10, true><<<(unsigned)std::min<long long>(N, (long long)h->sm_count * 8), kLatThreads,
                                                         ((FK + 1) & ~size_t(1)) * sizeof(float) + (kLatThreads / 32) * sizeof(double), st>>>(
                       h->cfg, points_dev, parts, hsplit, N, out_dev);
         else backend_logl_parts_kernel<<<grid, kBackThreads, wpb * FK * sizeof(double), st>>>(h->cfg, points_dev, parts, hsplit, N, out_dev);
@@ -744,7 +749,14 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev, int64_t N, double* 
         if (int rc = launch_frontend(h, pts, nn, h->coeff_scratch, st)) return rc;
         const long long warps_per_block = kBackThreads / 32;
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nn + warps_per_block - 1) / warps_per_block, (long long)h->sm_count * 16));
-        backend_logl_kernel<<<grid, kBackThreads, 0, st>>>(h->cfg, pts, h->coeff_scratch, nn, out_dev + n0);
+        // small batches of configurations the FAST back end covers: one CTA per point, one thread per observation
+        const bool fast_lat = nn <= h->opt_latency_max && h->fast_backend_ok && h->K == 10 && !h->opt_no_fast;
+        if (fast_lat)
+            backend_logl_parts_fast_kernel<10, false><<<(unsigned)std::min<long long>(nn, (long long)h->sm_count * 8), kLatThreads,
+                                                       ((FK + 1) & ~size_t(1)) * sizeof(float) + (kLatThreads / 32) * sizeof(double), st>>>(
+                h->cfg, pts, reinterpret_cast<const float*>(h->coeff_scratch), 1, nn, out_dev + n0);
+        else
+            backend_logl_kernel<<<grid, kBackThreads, 0, st>>>(h->cfg, pts, h->coeff_scratch, nn, out_dev + n0);
         CU(cudaGetLastError());
         h->launches += 1;
     }

@@ -61,6 +61,7 @@ struct nmma_b200_handle {
     nmma::DevCfg cfg{};
     bool fused_supported = false;
     bool tc_supported = false;
+    bool fast_backend_ok = false;      // direct filter maps on the uniform training grid: the fp32 per-observation term applies
     bool tc_front_supported = false;   // tensor-core front end in coefficient mode (any n_coeff <= 16, any filter mapping)
     long long opt_tc_front_min = 128;  // two-stage path: coefficients from the tensor-core kernel from this batch size
     double* coeff_scratch = nullptr;

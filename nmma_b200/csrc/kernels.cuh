@@ -168,7 +168,8 @@ coeff_gp_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, d
             }
         }
         __syncthreads();
-        for (int pair = warp; pair < F * K; pair += kGpThreads / 32) {
+        // small batches: the (filter, coefficient) pairs of a tile are spread over gridDim.y CTAs (one-point latency)
+        for (int pair = warp + (kGpThreads / 32) * blockIdx.y; pair < F * K; pair += (kGpThreads / 32) * gridDim.y) {
             const double q = cfg.gp_q[pair], ra = cfg.gp_ra[pair];
             const double* __restrict__ A = cfg.gpA + (size_t)pair * Ntr;
             double acc[kGpPts];
@@ -662,7 +663,8 @@ __device__ __forceinline__ const double* basis_src(const DevCfg& cfg, int f, int
 // (launch_tc.cu: launch_tc_coeff_parts) and are added in range order; the observation terms are added in a fixed order
 // (warp shuffles, then warp 0 over the warps' sums).
 constexpr int kLatThreads = 160;
-template <int K>
+// PARTS = false: `parts` is really the fp64 coefficient array [N][F*K] of a two-stage front end (GP surrogates, forced path 2).
+template <int K, bool PARTS>
 __global__ void __launch_bounds__(kLatThreads)
 backend_logl_parts_fast_kernel(const DevCfg cfg, const double* __restrict__ pts, const float* __restrict__ parts, int hsplit,
                                long long N, double* __restrict__ out) {
@@ -676,11 +678,15 @@ backend_logl_parts_fast_kernel(const DevCfg cfg, const double* __restrict__ pts,
         if (tid == 0) s_ok = 1;
         __syncthreads();
         for (int i = tid; i < FK; i += blockDim.x) {
-            const int f = i / K, k = i - f * K;
-            const float* p = parts + (((size_t)n * cfg.F + f) * hsplit) * K + k;
             float sum = 0.f;
-            for (int hs = 0; hs < hsplit; ++hs) sum += p[(size_t)hs * K];
-            sum += cfg.b2[i];
+            if constexpr (PARTS) {
+                const int f = i / K, k = i - f * K;
+                const float* p = parts + (((size_t)n * cfg.F + f) * hsplit) * K + k;
+                for (int hs = 0; hs < hsplit; ++hs) sum += p[(size_t)hs * K];
+                sum += cfg.b2[i];
+            } else {
+                sum = (float)reinterpret_cast<const double*>(parts)[(size_t)n * FK + i];
+            }
             if (!isfinite(sum)) s_ok = 0;
             s_cf[i] = sum;
         }
