@@ -357,14 +357,17 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                 const bool det = std::isfinite(h->o_s[k]) && std::isfinite(h->o_m[k]) && std::isfinite(tk);
                 int cls = kObsGeneral, i0 = -1, i1 = -1;
                 float wgt = 0.f;
+                const bool upper = !std::isfinite(h->o_s[k]) && std::isfinite(h->o_m[k]) && std::isfinite(tk);
                 if (det && sy_mode[g] == 0 && lim == INFINITY) {
                     cls = kObsSimple;
-                } else if (det && h->o_m[k] <= lim && !std::isnan(lim) && lim > -INFINITY) {
-                    // the support test m <= limit does not depend on the point; m > limit stays on the exact path (-inf)
+                } else if (upper || (det && h->o_m[k] <= lim && !std::isnan(lim) && lim > -INFINITY)) {
+                    // detections: the support test m <= limit does not depend on the point; m > limit stays on the exact
+                    // path (-inf).  Upper limits (norm.logsf) share the sigma_sys plumbing of the sampled class.
+                    const int fast_cls = upper ? kObsUpper : kObsSampled;
                     if (sy_mode[g] == 0) {
-                        cls = kObsSampled;   // constant budget behind a finite detection limit
+                        cls = fast_cls;      // constant budget (behind a finite detection limit / for an upper limit)
                     } else if (sy_mode[g] == 1) {
-                        cls = kObsSampled; i0 = i1 = sy_off[g];
+                        cls = fast_cls; i0 = i1 = sy_off[g];
                     } else if (sy_mode[g] == 2 && sy_nn[g] >= 2) {
                         // np.interp(t, nodes, values) with 'constant' ends (em/utils.py:667-670): fixed bracket and weight
                         const double* tn = &sy_t[sy_off[g]];
@@ -372,7 +375,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                         bool sorted = true;
                         for (int i = 0; i + 1 < nn; ++i) sorted = sorted && tn[i + 1] > tn[i];
                         if (sorted) {
-                            cls = kObsSampled;
+                            cls = fast_cls;
                             if (tk <= tn[0]) { i0 = i1 = sy_off[g]; }
                             else if (tk >= tn[nn - 1]) { i0 = i1 = sy_off[g] + nn - 1; }
                             else {

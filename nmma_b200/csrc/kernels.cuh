@@ -436,6 +436,7 @@ constexpr int kObsRec = 12;          // doubles per staged observation record: t
 constexpr int kObsGeneral = 0;       // fp64 obs_term: upper limits, mag > limit, anything unusual
 constexpr int kObsSimple = 1;        // detection, constant budget, no detection limit: everything staged on the host
 constexpr int kObsSampled = 2;       // detection with sampled / time-interpolated sigma_sys and / or a finite detection limit
+constexpr int kObsUpper = 3;         // upper limit (sigma_obs not finite): log Phi((mu - m) / sigma_sys) in fp32
 
 __host__ __device__ constexpr int fused_rw(int D, int K) { return (D + 1 + K + 3) / 4 * 4; }
 __host__ __device__ inline size_t fused_bslot(int K, int T) {
@@ -566,7 +567,7 @@ __device__ __forceinline__ double fast_obs_term(const DevCfg& cfg, const FastFil
         // SciPy gives NaN: both end as the sentinel (core/base.py:180-181)
         const float xq = (rf.y - mu) * rf.z;
         out += (double)fmaf(-0.5f * xq, xq, -rf.w);
-    } else if (cls.x == kObsSampled) {
+    } else if (cls.x == kObsSampled || cls.x == kObsUpper) {
         // sigma_sys at this observation time: the bracketing nodes and the weight are fixed per observation
         // (systematics.py:288-291 through np.interp with 'constant' ends); the node values are per point
         const int2 nd = *reinterpret_cast<const int2*>(rec + 9);     // right node, weight bits
@@ -583,19 +584,26 @@ __device__ __forceinline__ double fast_obs_term(const DevCfg& cfg, const FastFil
             ssys = (float)fma((double)__int_as_float(nd.y), syc.nv1 - syc.nv0, syc.nv0);
             general = !(isfinite(syc.nv0) && isfinite(syc.nv1));   // a dropped node changes the bracket: exact path
         }
-        const float s2 = fmaf(ssys, ssys, sl.x);
-        const float inv = rsqrtf(s2);
-        const float xq = (rf.y - mu) * inv;
-        // log(s2) through MUFU.LG2 (__logf: absolute error < 4e-7 for s2 of order one) -- the libm forms of
-        // this class (logf, erfcf, log1pf) were ~300 instructions per observation and made the back end
-        // the critical path of config 3 (profiles/r02_fused_tc_c3_summary.json)
-        float term = fmaf(-0.5f * xq, xq, -0.5f * __logf(s2) - (float)NMMA_NORM_PDF_LOGC);
-        if (sl.y < CUDART_INF_F) {   // truncation at the detection limit: - log Phi((lim - mu) / sigma)
-            const float bq = (sl.y - mu) * inv;
-            term -= fast_log_ndtr(bq);
+        if (cls.x == kObsUpper) {
+            // upper limit: norm.logsf(m, mu, sigma_sys) = log Phi((mu - m) / sigma_sys) (em_likelihood.py:224-250); mu = +inf
+            // (outside the model window) gives +inf -> 0, like the exact path
+            general = general || !(ssys > 0.f) || !(ssys < CUDART_INF_F);
+            if (!general) out += (double)fast_log_ndtr((mu - rf.y) / ssys);
+        } else {
+            const float s2 = fmaf(ssys, ssys, sl.x);
+            const float inv = rsqrtf(s2);
+            const float xq = (rf.y - mu) * inv;
+            // log(s2) through MUFU.LG2 (__logf: absolute error < 4e-7 for s2 of order one) -- the libm forms of
+            // this class (logf, erfcf, log1pf) were ~300 instructions per observation and made the back end
+            // the critical path of config 3 (profiles/r02_fused_tc_c3_summary.json)
+            float term = fmaf(-0.5f * xq, xq, -0.5f * __logf(s2) - (float)NMMA_NORM_PDF_LOGC);
+            if (sl.y < CUDART_INF_F) {   // truncation at the detection limit: - log Phi((lim - mu) / sigma)
+                const float bq = (sl.y - mu) * inv;
+                term -= fast_log_ndtr(bq);
+            }
+            general = general || !(s2 > 0.f) || !(s2 < CUDART_INF_F);
+            if (!general) out += (double)term;
         }
-        general = general || !(s2 > 0.f) || !(s2 < CUDART_INF_F);
-        if (!general) out += (double)term;
     }
     if (general) {
         const double so = rec[2];
