@@ -256,7 +256,8 @@ int nmma_b200_logl_sweep(nmma_b200_t* h, uint64_t seed, int64_t first_index, int
  *       "points_per_thread" (FFMA kernel: 0 auto, 1, 2, 4), "no_fast_backend" (1 = generic fp64 back end),
  *       "no_filter_split" (1 = tensor-core kernel keeps one CTA per 256-point super-tile on small batches),
  *       "pipeline_blocks" (row blocks of the nmma_b200_logl_host copy/compute pipeline, 1 = serial),
- *       "zero_copy" (1 = nmma_b200_logl_host lets the kernels read / write page-locked host memory for <= 256 rows). */
+ *       "zero_copy" (1 = nmma_b200_logl_host lets the kernels read / write page-locked host memory for <= 256 rows),
+ *       "cuda_graphs" (1 = nmma_b200_logl_host replays a captured CUDA graph per batch size on the latency path). */
 int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value);
 /* keys: "launches" (kernels launched by this handle so far), "last_path", "sm_count", "ctas_per_sm",
  *       "fused_supported", "tc_supported", "tc_front_supported", "gp_fused_supported", "algorithmic_flop_per_eval", "tc_executed_flop_per_eval". */

@@ -77,6 +77,9 @@ inline void tf32_split(float w, float* hi, float* lo) {
 
 int ensure_scratch(nmma_b200_t* h, size_t n_doubles) {
     if (n_doubles <= h->coeff_cap) return NMMA_B200_OK;
+    for (auto& g : h->lat_graphs) cudaGraphExecDestroy(g.exec);   // captured graphs hold the old scratch pointer
+    h->lat_graphs.clear();
+    h->lat_warm.clear();
     if (h->coeff_scratch) cudaFree(h->coeff_scratch);
     h->coeff_scratch = nullptr;
     h->coeff_cap = 0;
@@ -433,6 +436,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                                 gf_smem_bytes(h->Ntr, d) <= 227 * 1024;
     }
     h->dirty = false;
+    h->cfg_epoch += 1;   // captured graphs hold the old DevCfg by value
     return NMMA_B200_OK;
 }
 
@@ -477,6 +481,7 @@ int nmma_b200_destroy(nmma_b200_t* h) {
     cudaSetDevice(h->device);
     free_dev(h);
     if (h->coeff_scratch) cudaFree(h->coeff_scratch);
+    for (auto& g : h->lat_graphs) cudaGraphExecDestroy(g.exec);
     if (h->tc_parts) cudaFree(h->tc_parts);
     if (h->gp_parts) cudaFree(h->gp_parts);
     if (h->gp_tickets) cudaFree(h->gp_tickets);
@@ -778,6 +783,12 @@ static bool is_device_mem(const void* p) {
     return a.type == cudaMemoryTypeDevice;
 }
 
+static void drop_lat_graphs(nmma_b200_t* h) {
+    for (auto& g : h->lat_graphs) cudaGraphExecDestroy(g.exec);
+    h->lat_graphs.clear();
+    h->lat_warm.clear();
+}
+
 constexpr int64_t kZeroCopyMax = 256;   // rows up to which nmma_b200_logl_host skips the staging copies
 
 // Shared body of nmma_b200_logl_host (out_dev == false: `out_host` is host memory) and nmma_b200_logl_host_to_device
@@ -787,6 +798,7 @@ static int logl_host_impl(nmma_b200_t* h, const double* points_host, int64_t N, 
     // page-locked caller buffers are copied directly; pageable ones go through pinned staging
     const bool in_pinned = is_pinned_host(points_host);
     const bool out_pinned = out_dev || is_pinned_host(out_host);
+    if (nin > h->stage_cap_in || (!out_dev && nout > h->stage_cap_out)) drop_lat_graphs(h);
     if (nin > h->stage_cap_in) {
         if (h->stage_in_dev) cudaFree(h->stage_in_dev);
         if (h->stage_in_host) cudaFreeHost(h->stage_in_host);
@@ -824,6 +836,46 @@ static int logl_host_impl(nmma_b200_t* h, const double* points_host, int64_t N, 
         // it saves (73 vs 60 us per one-point call), so its rows are copied (one small DMA); the result is still written in
         // place.  The filter-split fused kernel (9 CTAs, one reader per point) keeps reading in place.
         if (h->tc_front_supported && N <= h->opt_latency_max && (h->opt_path == 0 || h->opt_path == 5)) {
+            if (h->opt_graphs) {
+                // One-point calls are launch-bound (a DMA and two kernels of ~10 us each): the sequence is captured once per
+                // batch size into a CUDA graph over the handle's own staging buffers and replayed with one launch call.
+                // The first call of a size runs un-captured (allocations, function attributes), the second captures.
+                if (!h->lat_graphs.empty() && h->lat_graphs[0].epoch != h->cfg_epoch) drop_lat_graphs(h);
+                nmma_b200_handle::LatGraph* g = nullptr;
+                for (auto& c : h->lat_graphs) if (c.N == N) g = &c;
+                const bool warm = std::find(h->lat_warm.begin(), h->lat_warm.end(), N) != h->lat_warm.end();
+                if (!g && warm) {
+                    cudaGraph_t graph = nullptr;
+                    cudaGraphExec_t exec = nullptr;
+                    const long long l0 = h->launches;
+                    bool ok = cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                    if (ok) {
+                        ok = cudaMemcpyAsync(h->stage_in_dev, h->stage_in_host, nin * sizeof(double), cudaMemcpyHostToDevice, h->own_stream) == cudaSuccess;
+                        ok = ok && nmma_b200_logl(h, h->stage_in_dev, N, h->stage_out_host, h->own_stream) == NMMA_B200_OK;
+                        ok = (cudaStreamEndCapture(h->own_stream, &graph) == cudaSuccess) && ok && graph != nullptr;
+                    }
+                    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                    if (graph) cudaGraphDestroy(graph);
+                    if (ok) {
+                        h->lat_graphs.push_back({N, h->cfg_epoch, exec, h->launches - l0});
+                        h->launches = l0;
+                        g = &h->lat_graphs.back();
+                    } else {
+                        cudaGetLastError();
+                        h->opt_graphs = 0;   // fall back to plain launches for the rest of this handle's life
+                    }
+                }
+                if (g) {
+                    if (src != h->stage_in_host) std::memcpy(h->stage_in_host, src, nin * sizeof(double));
+                    CU(cudaGraphLaunch(g->exec, h->own_stream));
+                    CU(cudaStreamSynchronize(h->own_stream));
+                    std::memcpy(out_host, h->stage_out_host, nout * sizeof(double));
+                    h->launches += g->launches;
+                    h->last_path = 5;
+                    return NMMA_B200_OK;
+                }
+                if (!warm) h->lat_warm.push_back(N);
+            }
             CU(cudaMemcpyAsync(h->stage_in_dev, src, nin * sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
             src = h->stage_in_dev;
         }
@@ -930,6 +982,7 @@ int nmma_b200_mags(nmma_b200_t* h, const double* points_dev, int64_t N, int appa
 int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     if (!h || !key) return NMMA_B200_ERR_ARG;
     const std::string k(key);
+    drop_lat_graphs(h);   // any knob may change which kernels a captured latency graph would have launched
     if (k == "path") { if (value < 0 || value > 5) return fail(h, NMMA_B200_ERR_ARG, "path must be 0 (auto), 1 (fused FFMA), 2 (two-stage), 3 (tensor core), 4 (fused GP) or 5 (latency: hidden-split tensor core + back end)"); h->opt_path = (int)value; }
     else if (k == "fused_min_points") h->opt_fused_min = value;
     else if (k == "tc_min_points") h->opt_tc_min = value;
@@ -942,6 +995,7 @@ int nmma_b200_set_option(nmma_b200_t* h, const char* key, int64_t value) {
     else if (k == "no_fast_backend") h->opt_no_fast = value ? 1 : 0;
     else if (k == "no_filter_split") h->opt_no_fsplit = value ? 1 : 0;
     else if (k == "zero_copy") h->opt_zero_copy = value ? 1 : 0;
+    else if (k == "cuda_graphs") h->opt_graphs = value ? 1 : 0;
     else if (k == "points_per_thread") { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, NMMA_B200_ERR_ARG, "points_per_thread must be 0 (auto), 1, 2 or 4"); h->opt_pt = (int)value; }
     else return fail(h, NMMA_B200_ERR_ARG, "unknown option '%s'", key);
     return NMMA_B200_OK;

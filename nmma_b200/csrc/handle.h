@@ -80,6 +80,12 @@ struct nmma_b200_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_in_stream = nullptr, copy_out_stream = nullptr;   // nmma_b200_logl_host copy/compute pipeline
     std::vector<cudaEvent_t> pipe_events;
+    // CUDA graphs of the latency path (nmma_b200_logl_host, N <= 256): copy + two kernels replayed with one launch call
+    struct LatGraph { int64_t N; unsigned long long epoch; cudaGraphExec_t exec; long long launches; };
+    std::vector<LatGraph> lat_graphs;
+    std::vector<int64_t> lat_warm;          // batch sizes that have run once un-captured at this epoch (allocations done)
+    unsigned long long cfg_epoch = 0;       // bumped whenever finalize() rebuilds the device configuration
+    int opt_graphs = 1;                     // set_option "cuda_graphs"
     int opt_pipeline = 6;             // row blocks of the host-buffer pipeline (set_option "pipeline_blocks"; 1 = serial)
     // ---- knobs / counters ----
     int opt_path = 0;
