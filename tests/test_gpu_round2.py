@@ -347,3 +347,43 @@ def test_observations_on_grid_nodes_and_range_ends(torch_cuda):
     ref = harness.oracle_logl(olik, fixed, pts, cols)
     for path, got in _paths(lik, pts, cols).items():
         print("on-node", path, assert_logl_close(got, ref))
+
+
+# ------------------------------------------------------------------------------------------------
+# latency path: CUDA-graph replay per batch size, invalidation on reconfiguration
+# ------------------------------------------------------------------------------------------------
+def test_latency_graph_replay_and_invalidation(torch_cuda):
+    """nmma_b200_logl_host, N <= 256: the first call of a size runs un-captured, the second captures a CUDA graph, later ones
+    replay it.  Replays must follow the inputs, survive other batch sizes in between, and be dropped when the configuration
+    (here: the detection limit) or an option changes."""
+    from nmma_b200 import synthetic as syn
+    from oracle import harness
+    lc_data, filters = syn.load_at2017gfo(data_tmax=14.0)
+    core = syn.random_model("Bu2019lm", filters, seed=0)
+    priors = syn.bu2019lm_prior()
+    lik, olik, fixed, cols = build_pair(core, "Bu2019lm", filters, filters, lc_data, priors)
+    pts, _ = priors.sample_array(64, np.random.default_rng(3), cols)
+    ref = harness.oracle_logl(olik, fixed, pts, cols)
+    eng = lik.sub_model.engine_for(cols)
+    launches0 = eng.get_info("launches")
+    for rep in range(4):                                            # un-captured, capture, replay, replay -- different rows each
+        for i in range(5):
+            got = eng.logl_host(pts[5 * rep + i:5 * rep + i + 1])
+            assert_logl_close(got, ref[5 * rep + i:5 * rep + i + 1])
+        assert_logl_close(eng.logl_host(pts[:17]), ref[:17])        # another size in between
+    assert eng.get_info("last_path") == 5
+    assert eng.get_info("launches") - launches0 == 2 * (4 * 5 + 4)  # replays count the kernels they launch
+    assert lik.log_likelihood(dict(zip(cols, pts[40]))) == pytest.approx(ref[40], rel=1e-4)
+    # an option change drops the graphs; the next calls go through another kernel family and then recapture
+    eng.set_option("path", 3)
+    assert_logl_close(eng.logl_host(pts[:1]), ref[:1])
+    eng.set_option("path", 0)
+    for _ in range(3):
+        assert_logl_close(eng.logl_host(pts[:1]), ref[:1])
+    # a new configuration (finite detection limit brighter than some detections: every point fails) must not replay the old graph
+    lik2, olik2, fixed2, cols2 = build_pair(core, "Bu2019lm", filters, filters, lc_data, priors, detection_limit=19.0)
+    eng2 = lik2.sub_model.engine_for(cols2)
+    for _ in range(3):
+        assert eng2.logl_host(pts[:1])[0] == SENTINEL
+    eng.set_option("cuda_graphs", 0)
+    assert_logl_close(eng.logl_host(pts[:3]), ref[:3])
