@@ -97,13 +97,24 @@ int launch_frontend(nmma_b200_t* h, const double* pts, long long N, double* coef
         coeff_mlp_kernel<<<grid, kCoeffThreads, 0, st>>>(h->cfg, pts, N, coeff);
     } else {
         const long long ntiles = (N + kGpPts - 1) / kGpPts;
-        const size_t smem = (size_t)kGpPts * h->Ntr * sizeof(double);
-        CU(cudaFuncSetAttribute(coeff_gp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ntiles, (long long)h->sm_count * 8));
+        // gf_pow needs 256 a log2(base) < 2^31: a <= 1e5 (finalize), and its tables 64 KB next to the r^2 tile
+        // Large batches only: the tables cap the residency at 3 CTAs per SM, which small grids of this lanes-over-rows
+        // kernel (4 chains per warp) pay for in latency hiding (profiles/r02_gp_threshold.txt: break-even at ~4096 points)
+        const bool gf = h->gp_alpha_ok && ntiles >= 2048 &&
+                        (size_t)kGpPts * h->Ntr * sizeof(double) + kGfLogBytes + kGfExpBytes <= 227 * 1024;
+        const size_t smem = (size_t)kGpPts * h->Ntr * sizeof(double) + (gf ? kGfLogBytes + kGfExpBytes : 0);
+        static size_t attr_smem[2] = {0, 0};
+        if (attr_smem[gf] < smem) {
+            if (gf) CU(cudaFuncSetAttribute(coeff_gp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CU(cudaFuncSetAttribute(coeff_gp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem[gf] = smem;
+        }
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ntiles, (long long)h->sm_count * (gf ? 3 : 8)));
         // few tiles: spread the F K (filter, coefficient) pairs of each over several CTAs, one pair per warp at most
         const long long pair_groups = ((long long)h->F * h->K + kGpThreads / 32 - 1) / (kGpThreads / 32);
         const unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>(pair_groups, (long long)h->sm_count * 4 / std::max<long long>(1, ntiles)));
-        coeff_gp_kernel<<<dim3(grid, gy), kGpThreads, smem, st>>>(h->cfg, pts, N, coeff);
+        if (gf) coeff_gp_kernel<true><<<dim3(grid, gy), kGpThreads, smem, st>>>(h->cfg, pts, N, coeff);
+        else coeff_gp_kernel<false><<<dim3(grid, gy), kGpThreads, smem, st>>>(h->cfg, pts, N, coeff);
     }
     CU(cudaGetLastError());
     h->launches += 1;
@@ -296,6 +307,8 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                 if (h->pmin[f * d + i] != h->pmin[i] || h->pmax[f * d + i] != h->pmax[i])
                     return fail(h, NMMA_B200_ERR_UNSUPPORTED, "GP path needs identical param_mins/maxs across filters");
         const size_t n = (size_t)F * K;
+        h->gp_alpha_ok = true;   // gf_pow takes rint(256 a log2(base)) from the low word of a double: a <= 1e5, the sklearn bound
+        for (double a : h->gpRa) h->gp_alpha_ok = h->gp_alpha_ok && a > 0.0 && a <= 1e5;
         std::vector<double> A(n * h->Ntr), q(n);
         for (size_t p = 0; p < n; ++p) {
             q[p] = 1.0 / (2.0 * h->gpRa[p] * h->gpRl[p] * h->gpRl[p]);
@@ -430,9 +443,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
                           tc_smem_bytes(K, T, c.S, nobs) <= 227 * 1024;
         // fused GP kernel: gf_pow takes rint(256 a log2(base)) from the low word of a double, i.e. needs it below 2^31:
         // a <= 1e5 (the sklearn bound of RationalQuadratic.alpha) leaves room for base < 2^80
-        bool gp_alpha_ok = true;
-        for (double a : h->gpRa) gp_alpha_ok = gp_alpha_ok && a > 0.0 && a <= 1e5;
-        h->gp_fused_supported = (h->kind == 1) && direct && gp_fused_has(d, K) && gp_alpha_ok &&
+        h->gp_fused_supported = (h->kind == 1) && direct && gp_fused_has(d, K) && h->gp_alpha_ok &&
                                 gf_smem_bytes(h->Ntr, d) <= 227 * 1024;
     }
     h->dirty = false;

@@ -37,40 +37,10 @@
 
 namespace nmma {
 
-constexpr int kGfTab = 256;
 constexpr int kGfWarps = 16;                   // one CTA per SM: 4 warps per sub-partition at <= 128 registers
-constexpr int kGfLogBytes = kGfTab * 8 * 16;   // {r_i, -log2 r_i} x 8 replicas
-constexpr int kGfExpBytes = kGfTab * 16 * 8;   // 2^(j/256) x 16 replicas
 
 inline size_t gf_smem_bytes(int Ntr, int d) {
     return (size_t)kGfLogBytes + kGfExpBytes + ((size_t)Ntr * d * sizeof(double) + 127) / 128 * 128;
-}
-
-// (1 + r2 q)^(-a) with na = -256 a.  `ltab` / `etab` already carry this lane's replica offset.
-// Valid for 256 a log2(base) < 2^31 (a <= 1e5, the sklearn bound, and base < 2^80; checked / documented in launch_gp.cu).
-__device__ __forceinline__ double gf_pow(double r2, double q, double na, const unsigned char* __restrict__ ltab,
-                                         const unsigned char* __restrict__ etab) {
-    const double base = fma(r2, q, 1.0);
-    const int hi = __double2hiint(base);
-    const double2 ent = *reinterpret_cast<const double2*>(ltab + ((hi >> 5) & 0x7f80));   // cell (hi >> 12) & 255, 128 B apart
-    // u = m r_i - 1 with m = base 2^-e: the exponent is taken off r_i instead (one integer add on its high word)
-    const double rs = __hiloint2double(__double2hiint(ent.x) + 0x3ff00000 - (hi & 0x7ff00000), __double2loint(ent.x));
-    const double ed = (double)((hi >> 20) - 1023);
-    const double u = fma(base, rs, -1.0);
-    double p = fma(-0.36067471452205946, u, 0.4808994921226281);
-    p = fma(p, u, -0.7213475204440083);
-    p = fma(p, u, 1.4426950408883954);
-    const double lg2 = fma(p, u, ent.y) + ed;
-    const double t = na * lg2;
-    const double s = t + 6755399441055744.0;          // 1.5 * 2^52: the low word of s is rint(t)
-    const double xr = t - (s - 6755399441055744.0);   // |xr| <= 1/2
-    const int k = max(__double2loint(s), -1020 * 256);   // underflow: the value becomes ~2^-1020 instead of a wrapped exponent
-    double g = fma(2.2393953277407236e-12, xr, 3.308302983832675e-9);
-    g = fma(g, xr, 3.665565596910102e-6);
-    g = fma(g, xr, 0.0027076061740622769);
-    const double e2 = *reinterpret_cast<const double*>(etab + ((k << 7) & 0x7f80));        // 2^((k & 255) / 256)
-    const double v = fma(e2, g * xr, e2);             // in [0.99, 2.01)
-    return __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));      // * 2^(k >> 8)
 }
 
 // The same arithmetic for the K pairs of one training row, written stage by stage so that the K dependency chains are in
@@ -135,18 +105,7 @@ fused_gp_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Ntr = cfg.Ntr, F = cfg.F;
     double* Xs = reinterpret_cast<double*>(smem + kGfLogBytes + kGfExpBytes);
-    for (int i = tid; i < kGfTab; i += blockDim.x) {
-        const float cf = 1.0f + ((float)i + 0.5f) / (float)kGfTab;   // centre of mantissa cell i, exact in fp32
-        const double r = (double)(1.0f / cf);                          // the table holds the log of exactly this value
-        const double2 ent = make_double2(r, -log2(r));
-        double2* le = reinterpret_cast<double2*>(smem) + i * 8;
-#pragma unroll
-        for (int rep = 0; rep < 8; ++rep) le[rep] = ent;
-        const double e = exp2((double)i / kGfTab);
-        double* ee = reinterpret_cast<double*>(smem + kGfLogBytes) + i * 16;
-#pragma unroll
-        for (int rep = 0; rep < 16; ++rep) ee[rep] = e;
-    }
+    gf_tabs_fill(smem, tid, blockDim.x);
     for (int i = tid; i < Ntr * D; i += blockDim.x) Xs[i] = cfg.gpX[i];
     __syncthreads();
     const unsigned char* ltab = smem + (lane & 7) * 16;

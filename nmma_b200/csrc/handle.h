@@ -71,6 +71,7 @@ struct nmma_b200_handle {
     unsigned int* gp_tickets = nullptr;
     size_t gp_parts_cap = 0, gp_tickets_cap = 0;
     bool gp_fused_supported = false;
+    bool gp_alpha_ok = false;         // every RationalQuadratic alpha in (0, 1e5]: gf_pow applies
     size_t coeff_cap = 0;
     double* stage_in_dev = nullptr;
     double* stage_out_dev = nullptr;

@@ -16,6 +16,56 @@
 
 namespace nmma {
 
+// ---------------------------------------------------------------------------------------------
+// gf_pow: (1 + r^2 q)^(-a) in 17 fp64 instructions with conflict-free replicated tables (design notes: gp_kernel.cuh).
+// Shared by the fused GP kernel and, when every alpha is within the sklearn bound, by coeff_gp_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGfTab = 256;
+constexpr int kGfLogBytes = kGfTab * 8 * 16;   // {r_i, -log2 r_i} x 8 replicas
+constexpr int kGfExpBytes = kGfTab * 16 * 8;   // 2^(j/256) x 16 replicas
+// `smem` = kGfLogBytes + kGfExpBytes of 128-byte aligned shared memory; caller synchronises afterwards
+__device__ __forceinline__ void gf_tabs_fill(unsigned char* smem, int tid, int nthreads) {
+    for (int i = tid; i < kGfTab; i += nthreads) {
+        const float cf = 1.0f + ((float)i + 0.5f) / (float)kGfTab;   // centre of mantissa cell i, exact in fp32
+        const double r = (double)(1.0f / cf);                          // the table holds the log of exactly this value
+        const double2 ent = make_double2(r, -log2(r));
+        double2* le = reinterpret_cast<double2*>(smem) + i * 8;
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) le[rep] = ent;
+        const double e = exp2((double)i / kGfTab);
+        double* ee = reinterpret_cast<double*>(smem + kGfLogBytes) + i * 16;
+#pragma unroll
+        for (int rep = 0; rep < 16; ++rep) ee[rep] = e;
+    }
+}
+// (1 + r2 q)^(-a) with na = -256 a.  `ltab` / `etab` already carry this lane's replica offset.
+// Valid for 256 a log2(base) < 2^31 (a <= 1e5, the sklearn bound, and base < 2^80; checked / documented in launch_gp.cu).
+__device__ __forceinline__ double gf_pow(double r2, double q, double na, const unsigned char* __restrict__ ltab,
+                                         const unsigned char* __restrict__ etab) {
+    const double base = fma(r2, q, 1.0);
+    const int hi = __double2hiint(base);
+    const double2 ent = *reinterpret_cast<const double2*>(ltab + ((hi >> 5) & 0x7f80));   // cell (hi >> 12) & 255, 128 B apart
+    // u = m r_i - 1 with m = base 2^-e: the exponent is taken off r_i instead (one integer add on its high word)
+    const double rs = __hiloint2double(__double2hiint(ent.x) + 0x3ff00000 - (hi & 0x7ff00000), __double2loint(ent.x));
+    const double ed = (double)((hi >> 20) - 1023);
+    const double u = fma(base, rs, -1.0);
+    double p = fma(-0.36067471452205946, u, 0.4808994921226281);
+    p = fma(p, u, -0.7213475204440083);
+    p = fma(p, u, 1.4426950408883954);
+    const double lg2 = fma(p, u, ent.y) + ed;
+    const double t = na * lg2;
+    const double s = t + 6755399441055744.0;          // 1.5 * 2^52: the low word of s is rint(t)
+    const double xr = t - (s - 6755399441055744.0);   // |xr| <= 1/2
+    const int k = max(__double2loint(s), -1020 * 256);   // underflow: the value becomes ~2^-1020 instead of a wrapped exponent
+    double g = fma(2.2393953277407236e-12, xr, 3.308302983832675e-9);
+    g = fma(g, xr, 3.665565596910102e-6);
+    g = fma(g, xr, 0.0027076061740622769);
+    const double e2 = *reinterpret_cast<const double*>(etab + ((k << 7) & 0x7f80));        // 2^((k & 255) / 256)
+    const double v = fma(e2, g * xr, e2);             // in [0.99, 2.01)
+    return __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));      // * 2^(k >> 8)
+}
+
+
 #ifdef NMMA_TWO_STAGE_TU  // the non-template two-stage kernels are compiled into api.cu only
 // ---------------------------------------------------------------------------------------------
 // Front end (MLP, latency mapping)
@@ -128,13 +178,19 @@ __device__ __forceinline__ double rq_pow(double base, double alpha, const RqTabs
     return __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));   // * 2^floor(k / 256), k <= 0
 }
 
+// GFPOW = true (every alpha within the sklearn bound, checked on the host): gf_pow with its replicated conflict-free
+// tables in the first kGfLogBytes + kGfExpBytes of the dynamic shared memory; else rq_pow (any alpha).
+template <bool GFPOW>
 __global__ void __launch_bounds__(kGpThreads)
 coeff_gp_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, double* __restrict__ coeff) {
-    extern __shared__ double r2s[];  // kGpPts * Ntr
+    extern __shared__ __align__(128) unsigned char gp_smem[];
+    double* r2s = reinterpret_cast<double*>(gp_smem + (GFPOW ? kGfLogBytes + kGfExpBytes : 0));  // kGpPts * Ntr
     __shared__ RqTabs tabs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = cfg.d, K = cfg.K, Ntr = cfg.Ntr, F = cfg.F;
-    rq_tabs_fill(tabs, tid);
+    if constexpr (GFPOW) gf_tabs_fill(gp_smem, tid, kGpThreads); else rq_tabs_fill(tabs, tid);
+    const unsigned char* ltab = gp_smem + (lane & 7) * 16;
+    const unsigned char* etab = gp_smem + kGfLogBytes + (lane & 15) * 8;
     const long long ntiles = (N + kGpPts - 1) / kGpPts;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long n0 = tile * kGpPts;
@@ -170,7 +226,7 @@ coeff_gp_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, d
         __syncthreads();
         // small batches: the (filter, coefficient) pairs of a tile are spread over gridDim.y CTAs (one-point latency)
         for (int pair = warp + (kGpThreads / 32) * blockIdx.y; pair < F * K; pair += (kGpThreads / 32) * gridDim.y) {
-            const double q = cfg.gp_q[pair], ra = cfg.gp_ra[pair];
+            const double q = cfg.gp_q[pair], ra = cfg.gp_ra[pair], na = -256.0 * ra;
             const double* __restrict__ A = cfg.gpA + (size_t)pair * Ntr;
             double acc[kGpPts];
 #pragma unroll
@@ -179,8 +235,9 @@ coeff_gp_kernel(const DevCfg cfg, const double* __restrict__ pts, long long N, d
                 const double a = A[t];
 #pragma unroll
                 for (int p = 0; p < kGpPts; ++p) {
-                    const double base = 1.0 + r2s[p * Ntr + t] * q;  // 1 + dists / (2 alpha)
-                    const double kv = rq_pow(base, ra, tabs);        // base ** -alpha
+                    double kv;                                       // (1 + dists / (2 alpha l^2)) ** -alpha
+                    if constexpr (GFPOW) kv = gf_pow(r2s[p * Ntr + t], q, na, ltab, etab);
+                    else kv = rq_pow(1.0 + r2s[p * Ntr + t] * q, ra, tabs);
                     acc[p] = fma(kv, a, acc[p]);
                 }
             }
