@@ -485,6 +485,7 @@ def gpu_arm(args):
         sync()
         w1 = time.perf_counter()
         launches = eng.get_info("launches") - l0
+        timed_path = eng.get_info("last_path")      # the kernel family of the TIMED launches (later small calls take others)
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
         # parity on the timed output: the parity rows head every rank's block of the last step's gathered vector
@@ -497,7 +498,7 @@ def gpu_arm(args):
                       "tolerance": 1e-4, "what": "rows of the last TIMED step's output (all ranks' blocks of the gathered vector)"}
             assert masks and err < 1e-4, f"{name}: GPU/oracle disagree on the timed output: {err}"
         res = {"ms_total": ms_total, "kern_ms": kern_ms, "launches": int(launches), "parity": parity, "window": (w0, w1),
-               "n": n, "P": P, "eng": eng, "lik": lik, "nrot": nrot}
+               "n": n, "P": P, "eng": eng, "lik": lik, "nrot": nrot, "path": timed_path}
         if with_e2e:
             hb = None
             if world > 1:
@@ -545,12 +546,12 @@ def gpu_arm(args):
         out = {"algorithmic_flop_per_eval": flop, "kernel_ms_per_launch": r["kern_ms"],
                "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}}
-        path = eng.get_info("last_path")
+        path = r["path"]
         if _SPECS[name]["kind"] == "gp":
             out.update({"bound": "fp64 (CUDA cores: F K Ntr kernel values (1 + r^2 q)^-alpha per evaluation)",
                         "achieved": achieved, "peak": pk["dfma"], "unit": "TFLOP/s", "frac": achieved / pk["dfma"],
                         "peak_source": "fp64 FMA micro-benchmark measured in this run (nmma_b200_dfma_peak)",
-                        "kernel": "fused_gp_logl_kernel" if eng.get_info("last_path") == 4 else "coeff_gp_kernel + backend_logl_kernel"})
+                        "kernel": "fused_gp_logl_kernel" if path == 4 else "coeff_gp_kernel + backend_logl_kernel"})
         elif path == 3:
             executed = eng.get_info("tc_executed_flop_per_eval")
             out.update({"bound": "tensor", "achieved": achieved, "peak": pk["tf32"], "unit": "TFLOP/s",
@@ -676,7 +677,7 @@ def gpu_arm(args):
         except Exception:  # noqa: BLE001
             pass
         roofline["traffic"] = traffic
-        last_path = eng.get_info("last_path")
+        last_path = main["path"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_total"] / args.steps, "higher_is_better": True,
