@@ -289,6 +289,24 @@ class EMTransientLikelihood(NMMALikelihood):
         return f"{self.__class__.__name__} based on {self.sub_model.__repr__()}"
 
     # ---- bilby contract -------------------------------------------------------------------------
+    def posterior_conversion(self, posterior_samples):
+        """Derived posterior columns (``nmma/em/em_likelihood.py:124-132``): total ejecta mass, GRB wing angle twins.
+        Works on anything indexable by key with array values (a pandas DataFrame, a dict of arrays)."""
+        ps = posterior_samples
+        if "log10_mej_dyn" in ps and "log10_mej_wind" in ps:
+            ps["log10_mej"] = np.log10(10 ** (ps["log10_mej_wind"]) + 10 ** (ps["log10_mej_dyn"]))
+        if "thetaWing" in ps and "thetaCore" in ps:
+            ps["alphaWing"] = ps["thetaWing"] / ps["thetaCore"]
+        elif "alphaWing" in ps and "thetaCore" in ps:
+            ps["thetaWing"] = ps["alphaWing"] * ps["thetaCore"]
+        return ps
+
+    def final_diagnostics(self, bestfit_params, args=None, result=None):
+        """The reference plots the best-fit light curve here (matplotlib, out of scope); this returns what the plot shows:
+        ``(observable_times, {filter: apparent magnitudes})`` of the best fit, evaluated on the GPU."""
+        params = self.parameter_conversion(dict(bestfit_params))
+        return self.sub_model.light_curve_model.gen_detector_lc(params)
+
     def log_likelihood(self, parameters=None):
         """``nmma/core/base.py:77-82``.  The conversion chain of the reference only adds derived keys
         (KNtheta, log10 twins); the device performs the same conversions from the sampled columns, so
