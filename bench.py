@@ -418,6 +418,10 @@ def gpu_arm(args):
     # nvidia-smi needs ~1 s to start: launch it now, keep the samples that fall inside the timed regions
     sampler = ClockSampler(local_rank) if rank == 0 else None
     torch.cuda.set_device(local_rank)
+    numa = None
+    if world > 1:      # after the CPU arm has forked its workers: staging buffers and copy threads on the GPU's own NUMA node
+        from nmma_b200.sharding import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     dev = torch.device(f"cuda:{local_rank}")
@@ -688,7 +692,8 @@ def gpu_arm(args):
                        "sharding": (f"contiguous row blocks x{world} (ShardedEvaluator), NCCL all-gather of logL on a side stream "
                                     f"under the next step's kernels") if world > 1 else "single GPU",
                        "l2": f"inputs rotate through {N_ROTATE} distinct batches ({N_ROTATE * M * P * 8 / 1e6:.0f} MB > 126 MB L2)",
-                       "kernel_path": roofline.get("kernel")},
+                       "kernel_path": roofline.get("kernel"),
+                       "cpu_affinity": f"rank 0 bound to the CPUs of its GPU's NUMA node ({numa})" if numa else "unchanged"},
             "e2e": {"value": total_pts * args.steps / main["e2e_s"], "unit": UNIT,
                     "h2d_bytes_per_step": total_pts * P * 8, "d2h_bytes_per_step": total_pts * 8,
                     "api": "EMTransientLikelihood.log_likelihood_batch -> nmma_b200_logl_host (pinned host buffers)" +

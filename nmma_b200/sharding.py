@@ -22,6 +22,34 @@ from typing import Callable, Optional, Tuple
 import numpy as np
 
 
+def bind_to_gpu_numa_node(device: int) -> Optional[str]:
+    """Pin this process to the CPUs local to ``cuda:device`` (``/sys/bus/pci/devices/<bus id>/local_cpulist``) so that its
+    page-locked buffers are allocated on, and its copies issued from, the GPU's own NUMA node.  With eight ranks pushing
+    48 MB per step through one host, remote-node staging memory is what end-to-end scaling loses first.  Returns the CPU list
+    it bound to, or None when the topology is not visible (containers without /sys, a restricted cpuset): never raises."""
+    import os
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed or allowed == os.sched_getaffinity(0):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return text
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
     """Contiguous block of rank ``rank``: sizes differ by at most one, earlier ranks take the extra."""
     base, rem = divmod(int(n), int(world_size))
