@@ -267,36 +267,64 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         // tensor-core operand tiles (tc_kernel.cuh): K-major, no swizzle, hi/lo split
         c.tc_nch = 0;
         c.tcpack = nullptr;
-        // the h_lo W_hi term runs on fp16 copies of W_hi / 2 (tc_kernel.cuh): weights outside the fp16 range keep the
-        // tensor-core path off (the FFMA kernel takes over)
-        bool w2_fp16_ok = true;
-        for (float w : h->W2) w2_fp16_ok = w2_fp16_ok && std::isfinite(w) && std::fabs(w) < 6.0e4f;
-        if (d + 1 <= 8 && K <= kTcN2 && w2_fp16_ok) {
+        // fp16 operands, brought into range by exact power-of-two scalings (tc_kernel.cuh header): row i of [W1; b1]
+        // times 2^-r_i (largest entry in [2^9, 2^10)), column k of W2 times 2^q_k (largest entry in [8, 16)), the
+        // remainder of W2 times 2^11; every weight = hi + lo with two fp16 values (lo may be subnormal: its absolute
+        // error is then 2^-25, i.e. < 2^-34 of the row / column maximum)
+        bool w_ok = true;
+        for (float w : h->W1) w_ok = w_ok && std::isfinite(w);
+        for (float w : h->b1) w_ok = w_ok && std::isfinite(w);
+        for (float w : h->W2) w_ok = w_ok && std::isfinite(w);
+        if (d + 1 <= 8 && K <= kTcN2 && w_ok) {
             int nch = (H + kTcChunk - 1) / kTcChunk;
-            nch = (nch + kTcGroup - 1) / kTcGroup * kTcGroup;  // whole layer-2 accumulation groups (and an even count)
+            nch = (nch + kTcGroup - 1) / kTcGroup * kTcGroup;  // whole layer-2 accumulation groups ...
+            nch = (nch + 1) / 2 * 2;                           // ... and an even count (two TMEM buffers per tile)
             c.tc_nch = nch;
-            std::vector<float> tp((size_t)F * nch * kTcChunkFloats, 0.f);
-            for (int f = 0; f < F; ++f)
+            std::vector<float> tp((size_t)F * nch * kTcChunkFloats, 0.f), xs((size_t)F * 8, 0.f), s2inv((size_t)F * kTcN2, 1.f);
+            auto pow2_scale = [](float vmax, int top) {   // 2^p with vmax 2^p in [2^(top-1), 2^top); 1 for an all-zero row
+                if (!(vmax > 0.f)) return 1.0f;
+                int e; std::frexp(vmax, &e);              // vmax = m 2^e, m in [0.5, 1)
+                return std::ldexp(1.0f, top - e);
+            };
+            for (int f = 0; f < F; ++f) {
+                float rs[8];   // 2^-r_i
+                for (int i = 0; i <= d; ++i) {
+                    float vmax = 0.f;
+                    for (int j = 0; j < H; ++j)
+                        vmax = std::max(vmax, std::fabs(i < d ? h->W1[((size_t)f * d + i) * H + j] : h->b1[(size_t)f * H + j]));
+                    rs[i] = pow2_scale(vmax, 10);
+                    xs[(size_t)f * 8 + i] = 1.0f / rs[i];
+                }
+                float cs[kTcN2];   // 2^q_k
+                for (int o = 0; o < K; ++o) {
+                    float vmax = 0.f;
+                    for (int j = 0; j < H; ++j) vmax = std::max(vmax, std::fabs(h->W2[((size_t)f * H + j) * K + o]));
+                    cs[o] = pow2_scale(vmax, 4);
+                    s2inv[(size_t)f * kTcN2 + o] = 1.0f / cs[o];
+                }
                 for (int j = 0; j < H; ++j) {
-                    float* ch = &tp[((size_t)f * nch + j / kTcChunk) * kTcChunkFloats];
+                    __half* ch = reinterpret_cast<__half*>(&tp[((size_t)f * nch + j / kTcChunk) * kTcChunkFloats]);
                     const int n = j % kTcChunk;
-                    for (int k = 0; k <= d; ++k) {
-                        const float w = (k < d) ? h->W1[((size_t)f * d + k) * H + j] : h->b1[(size_t)f * H + j];
-                        tf32_split(w, &ch[tc_b_index(kTcChunk, n, k)], &ch[kTcB1Floats + tc_b_index(kTcChunk, n, k)]);
+                    for (int i = 0; i <= d; ++i) {   // K slot 3 i + {0, 1, 2} pairs with the A slots {x_hi, x_lo, x_hi}
+                        const float w = rs[i] * (i < d ? h->W1[((size_t)f * d + i) * H + j] : h->b1[(size_t)f * H + j]);
+                        const __half whi = __float2half_rn(w), wlo = __float2half_rn(w - __half2float(whi));
+                        const __half slot[3] = {whi, whi, wlo};
+                        for (int q = 0; q < 3; ++q) {
+                            const int k = 3 * i + q;
+                            ch[(k / 16) * kTcB1Halfs + tc_b_index16(kTcChunk, n, k % 16)] = slot[q];
+                        }
                     }
-                    const int s = n / 8, kk = n % 8;
+                    __half* b2t = ch + kTcK1Max * kTcB1Halfs + (n / 16) * kTcB2Halfs;   // [W_hi rows 0..15 | W_lo' rows 16..31] x 16 hidden
                     for (int o = 0; o < K; ++o) {
-                        // halved (exact): the activation warps hand over 2 relu(v) = v + |v|, one FADD on the FMA pipe
-                        // instead of an FMNMX on the half-rate ALU pipe; products and sums are bit-identical
-                        const float w = 0.5f * h->W2[((size_t)f * H + j) * K + o];
-                        float* whi = &ch[2 * kTcB1Floats + s * 128 + tc_b_index(kTcN2, o, kk)];
-                        tf32_split(w, whi, &ch[2 * kTcB1Floats + kTcB2Floats + s * 128 + tc_b_index(kTcN2, o, kk)]);
-                        // fp16 copy of W_hi for the h_lo W_hi term (kind::f16, K = 16): W_hi has 11 significant bits, so the
-                        // copy is exact unless |w| < 2^-14
-                        __half* hb = reinterpret_cast<__half*>(&ch[2 * kTcB1Floats + 2 * kTcB2Floats]);
-                        hb[(n / 16) * 256 + tc_b_index16(kTcN2, o, n % 16)] = __float2half_rn(*whi);
+                        const float w = cs[o] * h->W2[((size_t)f * H + j) * K + o];
+                        const __half whi = __float2half_rn(w);
+                        b2t[tc_b_index16(2 * kTcN2, o, n % 16)] = whi;
+                        b2t[tc_b_index16(2 * kTcN2, kTcN2 + o, n % 16)] = __float2half_rn((w - __half2float(whi)) * 2048.0f);
                     }
                 }
+            }
+            if (int rc = upload(h, xs, &c.tc_xs)) return rc;
+            if (int rc = upload(h, s2inv, &c.tc_s2inv)) return rc;
             if (int rc = upload(h, tp, &c.tcpack)) return rc;
         }
     } else {
@@ -1029,9 +1057,10 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value) {
         else if (h->kind == 1) *value = (int64_t)h->Ntr * 3 * h->d + (int64_t)h->F * h->K * h->Ntr * 8 + (int64_t)h->F * 2 * h->T * h->K;
         else return fail(h, NMMA_B200_ERR_STATE, "no surrogate configured");
     } else if (k == "tc_executed_flop_per_eval") {
-        // tensor-core kernel: per 32-hidden chunk and point 3 layer-1 MMAs (N=32, K=8) + 12 layer-2 MMAs (N=16, K=8)
+        // tensor-core kernel: per chunk and point 1-2 layer-1 MMAs (N = chunk, K = 16) + per 16 hidden units one N = 32 MMA
+        // (h_hi [W_hi | W_lo']) and one N = 16 MMA (h_lo W_hi), K = 16, kind::f16
         if (int rc = finalize(h, false)) return rc;
-        *value = (int64_t)h->F * h->cfg.tc_nch * (3LL * 2 * kTcChunk * 8 + 2LL * kTcKSteps * 2 * kTcN2 * 8 + 1LL * kTcKSteps16 * 2 * kTcN2 * 16);
+        *value = (int64_t)h->F * h->cfg.tc_nch * ((3 * (h->d + 1) <= 16 ? 1LL : 2LL) * 2 * kTcChunk * 16 + 1LL * kTcKSteps * 2 * (3 * kTcN2) * 16);
     } else return fail(h, NMMA_B200_ERR_ARG, "unknown info key '%s'", key);
     return NMMA_B200_OK;
 }

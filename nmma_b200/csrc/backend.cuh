@@ -37,8 +37,11 @@ struct DevCfg {
     // MLP front end
     const float* wpack;   // F*HP*RW: row j = [W1[0..d-1][j], b1[j], W2[j][0..K-1], 0-pad]
     const float* b2;      // F*K
-    // tensor-core front end: per (filter, 48-hidden chunk) kTcChunkFloats = B1hi | B1lo | B2hi | B2lo operand tiles
+    // tensor-core front end (tc_kernel.cuh): per (filter, chunk of hidden units) kTcChunkFloats of fp16 B tiles
+    // B1[2 k-steps] | B2[k-steps] = [W_hi | 2^11 W_lo], all scaled into the fp16 range by exact powers of two
     const float* tcpack;  // F*tc_nch*kTcChunkFloats
+    const float* tc_xs;   // F*8   2^r_i: multiplier of scaled input i (i = d: the bias "input" 1) matching row i of the staged W1
+    const float* tc_s2inv;// F*16  2^-q_k: undoes the scaling of column k of the staged W2
     int tc_nch;           // chunks per filter (even)
     // GP front end
     const double* gpX;    // Ntr*d

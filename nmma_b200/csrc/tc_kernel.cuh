@@ -1,32 +1,41 @@
 // Tensor-core throughput kernel: the surrogate MLP on tcgen05 (5th-gen tensor cores, accumulators and the
-// activation operand in TMEM), 3xTF32 split precision, fused with the fp64 likelihood back end.
+// activation operand in TMEM), split-precision fp16 operands (kind::f16), fused with the fp64 likelihood back end.
 //
 // Why split precision: single-pass TF32/BF16 misses the 1e-3 mag budget by two orders of magnitude
-// (profiles/r01_tc_numerics.txt); with a = a_hi + a_lo, b = b_hi + b_lo (hi = top 19 bits, which is exactly what the
-// tensor core reads from an fp32 operand of kind::tf32) the three products a_hi*b_hi + a_lo*b_hi + a_hi*b_lo carry
-// ~2^-21 relative error, the same order as fp32 FFMA.  The tensor core adds into its fp32 accumulator with
-// round-toward-zero (profiles/r01_tc_probe.txt), so the large layer-2 products h_hi*W_hi accumulate in chains of 12
-// MMAs (one 96-hidden group) whose partials the CUDA cores sum with round-to-nearest adds; the two cross terms are
-// 2^-11 smaller and accumulate over the whole filter in a separate accumulator, where the truncation bias is below
-// 2e-8 relative.
+// (profiles/r01_tc_numerics.txt); with a = a_hi + a_lo, b = b_hi + b_lo (fp16 halves: 11 + 11 significant bits) the
+// three products a_hi*b_hi + a_lo*b_hi + a_hi*b_lo carry ~2^-21 relative error, the order of fp32 FFMA
+// (tools/tc_numerics.py "f16x3": on the trained fixture weights it is as close to fp64 as NumPy's fp32).  fp16 has a
+// 5-bit exponent, so every operand is brought into range by EXACT power-of-two scalings:
+//   * layer 1: row i of [W1; b1] is staged times 2^-r_i so that its largest entry is in [2^9, 2^10) and input i is
+//     multiplied by 2^r_i (cfg.tc_xs); per point and filter the whole input row is scaled by 2^e with
+//     2^e sum_i |x_i 2^r_i| in [8, 16), so 2^e relu(v) < 2^14 whatever the point is (ReLU is positively homogeneous:
+//     the coefficients are multiplied by 2^-e at the end);
+//   * layer 2: column k of W2 is staged times 2^q_k (largest entry in [8, 16), cfg.tc_s2inv = 2^-q_k), its fp16
+//     remainder times 2^11; products of two fp16 values are exact in the fp32 accumulator.
+// The hi/lo split of h costs 2 CUDA-core instructions per hidden unit and point (3.5 with tf32 operands, round 1):
+//   hi2 = cvt.rz.relu.f16x2.f32 (v1, v0)         ReLU and round-toward-zero in one F2FP, so that v - hi >= 0 for v > 0
+//   l   = fma.rn.f32.f16 (hi, -1, v)             FHFMA: fp16 operand taken straight from the packed register
+//   lo2 = cvt.rn.relu.f16x2.f32 (l1, l0)         for v < 0: hi = 0, l = v < 0 -> 0
+// The tensor core adds into its fp32 accumulator with round-toward-zero (profiles/r01_tc_probe.txt), so layer 2
+// accumulates in chains of kTcGroup chunks whose partials the CUDA cores sum with round-to-nearest adds.
 //
-// What bounds it (profiles/r01_tc_experiments.md): not the tensor pipe (30 % active), not TMEM bandwidth (tools/tmem_bw.cu:
-// > 600 B/clk/SM for the ld + 2 st mix, the kernel moves ~60) and not the back end, but the latency of the per-chunk
-// hand-offs (mbarrier wake-up, tcgen05.ld / st + wait, tcgen05.commit): the bare skeleton of one chunk step costs ~700
-// cycles per tile.  Hence the chunk is as wide as TMEM allows: 48 hidden units, with h written back in place over the
-// layer-1 accumulator (32-hidden chunks with a separate h buffer: 151 M evals/s; 48 in place: 173 M).
+// What bounds it (profiles/r01_tc_experiments.md): not the tensor pipe, not TMEM bandwidth and not the back end, but the
+// per-chunk hand-offs (mbarrier wake-up, tcgen05.ld / st + wait, MMA issue by one thread, tcgen05.commit) and the
+// activation warps' instruction stream.  Hence: h_hi / h_lo go back IN PLACE over the layer-1 accumulator they came
+// from (one tcgen05.st per 32 hidden units), [W_hi | 2^11 W_lo] is ONE N = 32 B tile (h_hi needs one MMA per 16 hidden
+// units for both terms), and K = 16 per MMA: 9 MMAs per 64-hidden chunk instead of 23 with tf32 operands.
 //
 // Work decomposition (one persistent CTA per SM, 20 warps, two 128-point tiles in flight):
 //   warps 0-3 / 4-7    activation warps of tile 0 / 1: thread = one parameter point = one TMEM lane.  Per filter they
-//                      write the scaled inputs as the layer-1 A operand (TMEM); per 48-hidden chunk they read the
-//                      layer-1 accumulator (tcgen05.ld), apply ReLU, split into hi/lo, write h back in place and h_lo
-//                      beside it (tcgen05.st, the layer-2 A operands) and sum the layer-2 group partials; the K
+//                      write the scaled, split inputs as the layer-1 A operand (TMEM); per chunk they read the
+//                      layer-1 accumulator (tcgen05.ld), apply ReLU + split, write [h_hi | h_lo] back in place
+//                      (tcgen05.st, the layer-2 A operands) and sum the layer-2 group partials; the K
 //                      coefficients go to shared memory.
-//   warps 8 / 9        MMA issuer of tile 0 / 1 (one elected lane): per chunk D2 = [h_hi | h_lo] . W2^T (18 MMAs,
-//                      128x16x8) and, two chunks ahead, D1 = [x_hi,1 | x_lo] . [W1;b1]^T (3 MMAs, 128x48x8); A from
-//                      TMEM, B from shared memory.
-//   warp 10            TMA producer: 9 KB weight chunks (cp.async.bulk) into a shared-memory ring, basis packs per filter.
-//   warp 11            TMEM allocation / release.
+//   warps 8 / 9        MMA issuer of tile 0 / 1 (one elected lane): per chunk D2 += h_hi . [W_hi | W_lo']^T (N = 32) and
+//                      D2[0:16] += h_lo . W_hi^T (N = 16), and, two chunks ahead, D1 = A1 . B1^T (1-2 MMAs, N = chunk);
+//                      A from TMEM, B from shared memory.
+//   warp 10            TMA producer: 8 KB weight chunks (cp.async.bulk) into a shared-memory ring, basis packs per filter.
+//   warp 11            TMEM allocation / release, watchdog.
 //   warps 12-15/16-19  back-end warps of tile 0 / 1: thread = one point; reconstruction, interpolation and likelihood
 //                      (kernels.cuh: fused_filter_logl) for the filter whose coefficients the activation warps just
 //                      finished, overlapping the next filter's MLP.
@@ -43,32 +52,32 @@ constexpr int kTcActWarps = 8;
 constexpr int kTcBackWarp0 = 12;
 constexpr int kTcTile = 128;                 // points per tile = TMEM lanes
 constexpr int kTcTiles = 2;                  // tiles in flight per CTA
-constexpr int kTcChunk = 64;                 // hidden units per chunk = per act <-> issuer hand-off (N of the layer-1 MMA)
-constexpr int kTcBlk = 16;                   // columns per ReLU/split/store block of the activation warps (8: -1 %, 32+16: -2 %)
-constexpr int kTcKSteps = kTcChunk / 8;      // kind::tf32 layer-2 MMAs (K = 8) per chunk and term
-constexpr int kTcKSteps16 = kTcChunk / 16;   // kind::f16 layer-2 MMAs (K = 16) per chunk
-constexpr int kTcN2 = 16;                    // layer-2 MMA N (n_coeff padded)
-constexpr int kTcB1Floats = kTcChunk * 8;    // one layer-1 B tile: [64 hidden] x [8 = d inputs, bias, pad]
-constexpr int kTcB2Floats = kTcKSteps * kTcN2 * 8;      // tf32 layer-2 B tiles of one chunk: 8 k-steps x [16 coeff] x [8 hidden]
-constexpr int kTcB2HFloats = kTcKSteps16 * kTcN2 * 8;   // fp16 W_hi tiles: 4 k-steps x [16 coeff] x [16 hidden] halfs
-constexpr int kTcChunkFloats = 2 * kTcB1Floats + 2 * kTcB2Floats + kTcB2HFloats;   // B1hi | B1lo | B2hi | B2lo | B2hi(fp16) = 14 KB
+#ifndef TCV_CHUNK
+#define TCV_CHUNK 64
+#endif
+constexpr int kTcChunk = TCV_CHUNK;          // hidden units per chunk = per act <-> issuer hand-off (N of the layer-1 MMA)
+constexpr int kTcBlk = (kTcChunk % 32 == 0) ? 32 : 16;   // columns per ReLU/split/store block: [h_hi pairs | h_lo pairs] in place
+constexpr int kTcKSteps = kTcChunk / 16;     // kind::f16 layer-2 k-steps (K = 16) per chunk
+constexpr int kTcN2 = 16;                    // layer-2 MMA N per term (n_coeff padded)
+constexpr int kTcK1Max = 2;                  // layer-1 k-steps staged (3 (d + 1) slots: d <= 4 uses one, d <= 7 two)
+constexpr int kTcB1Halfs = kTcChunk * 16;    // one layer-1 B tile: [chunk hidden] x [16 K slots] fp16
+constexpr int kTcB2Halfs = 2 * kTcN2 * 16;   // one layer-2 B tile: [W_hi (16 coeff) | 2^11 W_lo (16 coeff)] x [16 hidden] fp16
+constexpr int kTcChunkFloats = (kTcK1Max * kTcB1Halfs + kTcKSteps * kTcB2Halfs) / 2;   // B1[0] | B1[1] | B2[k-steps] = 8 KB at 64
 constexpr uint32_t kTcChunkBytes = kTcChunkFloats * 4;
-constexpr int kTcStages = 6;                 // weight ring depth (84 KB)
-// TMEM columns of one tile (tile t at column 256 t).  The hand-off latency per chunk is fixed (~700 cycles,
-// profiles/r01_tc_experiments.md), so the chunk is as wide as 256 columns allow: h goes back IN PLACE over the layer-1
-// accumulator it came from, and h_lo (the 2^-11-relative remainder, which needs 11 bits, not 24) is packed as fp16
-// pairs and multiplied by an fp16 copy of W_hi with kind::f16 MMAs: 2 x (64 + 32) columns per tile.
-constexpr uint32_t kColD1 = 0;               // 2 x 64  layer-1 accumulators, overwritten by 2 relu(h) (the tensor core reads
-                                             //         its top 19 bits = h_hi as the layer-2 A operand)
-constexpr uint32_t kColA2L = 128;            // 2 x 32  h_lo as fp16 pairs (column j = hidden units 2j, 2j+1)
-constexpr uint32_t kColD2 = 192;             // 2 x 16  layer-2 h_hi*W_hi partials, double buffered by accumulation group
-constexpr uint32_t kColD2X = 240;            // 16      layer-2 cross terms h_lo*W_hi + h_hi*W_lo of the whole filter
+constexpr int kTcStages = 6;                 // weight ring depth
+// TMEM columns of one tile (tile t at column 256 t): everything layer 2 reads is written IN PLACE over the layer-1
+// accumulator block it came from (block of kTcBlk columns -> kTcBlk / 2 columns of h_hi fp16 pairs, then kTcBlk / 2 of h_lo).
+constexpr uint32_t kColD1 = 0;                       // 2 x chunk  layer-1 accumulators / layer-2 A operands
+constexpr uint32_t kColD2 = 2 * kTcChunk;            // 2 x 32     layer-2 partials [h W_hi | h_hi W_lo'], double buffered by group
+constexpr uint32_t kColA1 = 2 * kTcChunk + 64;       // 16         layer-1 A operand: fp16 pairs, 8 columns per k-step
+static_assert(kColA1 + 16 <= 256, "TMEM columns per tile");
+static_assert(kTcChunk % 16 == 0 && kTcChunk >= 16 && kTcChunk <= 256, "layer-1 MMA N");
 #ifndef TCV_GROUP
 #define TCV_GROUP 2
 #endif
-constexpr int kTcGroup = TCV_GROUP;          // chunks per layer-2 accumulation chain (8 k-step MMAs each, RZ accumulate)
-constexpr uint32_t kColA1H = 224;            // 8       [x_hi, 1, 0..]
-constexpr uint32_t kColA1L = 232;            // 8       [x_lo, 0, 0..]
+constexpr int kTcGroup = TCV_GROUP;          // chunks per layer-2 accumulation chain (2 kTcKSteps MMAs each, RZ accumulate)
+// TMEM column (relative to the chunk buffer) of the h_hi pairs of layer-2 k-step s; its h_lo pairs are kTcBlk / 2 further
+__host__ __device__ constexpr uint32_t tc_a2_col(int s) { return (uint32_t)(kTcBlk * (s / (kTcBlk / 16)) + 8 * (s % (kTcBlk / 16))); }
 
 // ---- tcgen05 wrappers (PTX forms as in cute/arch/mma_sm100_umma.hpp, copy_sm100.hpp, tmem_allocator_sm100.hpp) ----
 __device__ __forceinline__ bool elect_one() {
@@ -106,14 +115,26 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// v <- 2 relu(v) (= v + |v|: one FADD on the FMA pipe instead of an FMNMX on the half-rate ALU pipe; W2 is staged halved,
-// api.cu), lo <- its low part below the 19 bits the tensor core reads.
-__device__ __forceinline__ void relu_split(uint32_t& v, uint32_t& lo) {
-    const float vj = __uint_as_float(v);
-    const float h = vj + fabsf(vj);
-    const float hh = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
-    v = __float_as_uint(h);
-    lo = __float_as_uint(h - hh);
+// ReLU + hi/lo split of two layer-1 outputs into fp16 pairs (.x = low half = even hidden unit), 4 instructions:
+// hi = RZ(relu(v)) (one F2FP.RELU..RZ), v - hi in fp32 with the fp16 operand taken from the packed register (two FHFMA;
+// mixed-precision fma, PTX ISA 8.6 / sm_100), lo = RN(relu(v - hi)) (one F2FP.RELU): RZ makes v - hi >= 0 for v > 0, and
+// for v <= 0 hi = 0 and v - hi = v <= 0 -> 0.
+__device__ __forceinline__ void relu_split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    float l0, l1;
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+    asm("{\n\t.reg .b16 a, b, m;\n\t"
+        "mov.b32 {a, b}, %2;\n\t"
+        "mov.b16 m, 0xBC00;\n\t"   // -1.0
+        "fma.rn.f32.f16 %0, a, m, %3;\n\t"
+        "fma.rn.f32.f16 %1, b, m, %4;\n\t}"
+        : "=f"(l0), "=f"(l1)
+        : "r"(hi), "f"(v0), "f"(v1));
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l1), "f"(l0));
+}
+// round-to-nearest hi/lo split of a (range-checked) fp32 value into two fp16 values
+__device__ __forceinline__ void split_f16(float a, __half& hi, __half& lo) {
+    hi = __float2half_rn(a);
+    lo = __float2half_rn(a - __half2float(hi));
 }
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi,
                                            uint32_t idesc, uint32_t accumulate) {
@@ -303,34 +324,53 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             const long long n = (item / nparts) * SUPER + (long long)t * kTcTile + pidx;
             const double* row = pts + (n < N ? n : 0) * cfg.P;
             for (int f = TC_PART_F0(item), f1 = TC_PART_F1(item); f < f1; ++f, ++vseq) {
-                // ---- layer-1 A operand: [x_hi, 1, 0.. | x_lo, 0, 0..] (fp64 scaling, fp32 cast like Keras) ----
+                // ---- layer-1 A operand (fp64 scaling, fp32 cast like Keras; then the exact power-of-two scalings of the
+                //      header comment and the fp16 hi/lo split): K slot 3 i + {0, 1, 2} = {hi_i, lo_i, hi_i} ----
                 bool okx = true;
+                float inv_sc = 1.f;
                 {
-                    uint32_t ah[8], al[8];
+                    float xv[8];
+                    float S = 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        float xv = 0.f;
+                        xv[i] = 0.f;
                         if (i < cfg.d) {
                             const double xs = scaled_input(cfg, f, i, row);
                             okx = okx && isfinite(xs);
-                            xv = (float)xs;
+                            xv[i] = (float)xs * cfg.tc_xs[f * 8 + i];
                         } else if (i == cfg.d) {
-                            xv = 1.0f;
+                            xv[i] = cfg.tc_xs[f * 8 + i];
                         }
-                        const float xh = __uint_as_float(__float_as_uint(xv) & 0xFFFFE000u);
-                        ah[i] = __float_as_uint(xv);
-                        al[i] = __float_as_uint(xv - xh);
+                        S += fabsf(xv[i]);
                     }
-                    tmem_st8(tbase + kColA1H, ah);
-                    tmem_st8(tbase + kColA1L, al);
+                    // 2^e S in [8, 16): e = 3 - ilogb(S), from the exponent field (clamped: a degenerate S only costs accuracy)
+                    okx = okx && isfinite(S);
+                    uint32_t eb = (__float_as_uint(S) >> 23) & 0xFFu;
+                    eb = eb < 24u ? 24u : (eb > 230u ? 230u : eb);
+                    const float sc = okx ? __uint_as_float((257u - eb) << 23) : 0.f;
+                    inv_sc = __uint_as_float((eb - 3u) << 23);
+                    __half hs[16 * kTcK1Max];
+#pragma unroll
+                    for (int i = 0; i < 16 * kTcK1Max; ++i) hs[i] = __ushort_as_half((unsigned short)0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        __half hi, lo;
+                        split_f16(okx ? xv[i] * sc : 0.f, hi, lo);
+                        hs[3 * i] = hi; hs[3 * i + 1] = lo; hs[3 * i + 2] = hi;
+                    }
+                    uint32_t a1[8 * kTcK1Max];
+#pragma unroll
+                    for (int i = 0; i < 8 * kTcK1Max; ++i)
+                        a1[i] = (uint32_t)__half_as_ushort(hs[2 * i]) | ((uint32_t)__half_as_ushort(hs[2 * i + 1]) << 16);
+                    tmem_st16(tbase + kColA1, a1);
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->a1_full[t]);
                 }
-                float acc[K];
+                float acc[K], accx[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc[k] = 0.f;
+                for (int k = 0; k < K; ++k) { acc[k] = 0.f; accx[k] = 0.f; }
                 const uint32_t ubase = vseq * half;
 #pragma unroll 2
                 for (int c = 0; c < NCH; ++c) {
@@ -339,68 +379,80 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     uint32_t v[kTcChunk];
                     mbar_wait_spin(&bars->d1_full[t][b], u & 1);
                     tc_fence_after();
-                    tmem_ld32(tbase + kColD1 + kTcChunk * b, v);
-                    tmem_ld32(tbase + kColD1 + kTcChunk * b + 32, v + 32);
-                    tmem_wait_ld();
-                    if (c >= 2) {
-                        // L2 of chunk c-2 done: its h_lo buffer is free (D1[b] was already rewritten by layer 1 of this
-                        // chunk, queued behind it); if it closed a group, the partial is complete
-                        mbar_wait_spin(&bars->a2_free[t][b], (u - 1) & 1);
-                        tc_fence_after();
-                        if (((c - 2) & (kTcGroup - 1)) == kTcGroup - 1) {
-                            uint32_t part[16];
-                            tmem_ld16(tbase + kColD2 + 16 * (((c - 2) / kTcGroup) & 1), part);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
-                        }
-                    }
-                    // ReLU + hi/lo split in kTcBlk-column blocks, h back in place and h_lo (fp16 pairs) beside it: the stores
-                    // of one block are in flight while the next block is computed
 #pragma unroll
                     for (int blk = 0; blk < kTcChunk / kTcBlk; ++blk) {
-                        uint32_t pk[kTcBlk / 2];
+                        if constexpr (kTcBlk == 32) tmem_ld32(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, v + kTcBlk * blk);
+                        else tmem_ld16(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, v + kTcBlk * blk);
+                    }
+                    tmem_wait_ld();
+                    // ReLU + hi/lo split in kTcBlk-column blocks, [h_hi pairs | h_lo pairs] back in place: the store of one
+                    // block is in flight while the next block is computed
+#pragma unroll
+                    for (int blk = 0; blk < kTcChunk / kTcBlk; ++blk) {
+                        uint32_t o[kTcBlk];
 #ifndef TCV_NO_ALU   // TCV_*: compile-time timing experiments (tools/build_variants.py, profiles/r01_tc_experiments.md);
                      // a library built with any of them returns wrong numbers and only serves to time the skeleton
 #pragma unroll
-                        for (int j = 0; j < kTcBlk; j += 2) {
-                            uint32_t l0, l1;
-                            relu_split(v[kTcBlk * blk + j], l0);
-                            relu_split(v[kTcBlk * blk + j + 1], l1);
-                            const __half2 hp = __floats2half2_rn(__uint_as_float(l0), __uint_as_float(l1));  // .x = low half
-                            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
-                        }
+                        for (int j = 0; j < kTcBlk / 2; ++j)
+                            relu_split_f16x2(__uint_as_float(v[kTcBlk * blk + 2 * j]), __uint_as_float(v[kTcBlk * blk + 2 * j + 1]),
+                                             o[j], o[kTcBlk / 2 + j]);
 #else
 #pragma unroll
-                        for (int j = 0; j < kTcBlk / 2; ++j) pk[j] = v[kTcBlk * blk + j];
+                        for (int j = 0; j < kTcBlk; ++j) o[j] = v[kTcBlk * blk + j];
 #endif
-                        tmem_st16(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, v + kTcBlk * blk);
-#ifndef TCV_NO_STLO
-                        tmem_st8(tbase + kColA2L + (kTcChunk / 2) * b + (kTcBlk / 2) * blk, pk);
-#endif
+                        if constexpr (kTcBlk == 32) tmem_st32(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, o);
+                        else tmem_st16(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, o);
+                    }
+                    if (c >= 2 && ((c - 2) & (kTcGroup - 1)) == kTcGroup - 1) {
+                        // layer 2 of chunk c - 2 is complete (layer 1 of this chunk was queued behind it and d1_full has
+                        // fired); it closed a group: add its partials.  The issuer reuses that accumulator only after
+                        // this warp's a2_full of a later chunk.
+                        mbar_wait_spin(&bars->a2_free[t][b], (u - 1) & 1);
+                        tc_fence_after();
+                        uint32_t part[16], px[16];
+                        const uint32_t d2 = tbase + kColD2 + 32 * (((c - 2) / kTcGroup) & 1);
+                        tmem_ld16(d2, part);
+                        tmem_ld16(d2 + 16, px);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            acc[k] += __uint_as_float(part[k]);
+                            accx[k] += __uint_as_float(px[k]);
+                        }
                     }
                     tmem_wait_st();
                     tc_fence_before();  // orders the D1 / D2 loads and the operand stores before the issuer's next MMAs
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->a2_full[t][b]);
                 }
-                // drain: the last group's partial and the cross terms (NCH is a multiple of the group size)
+                // drain: the last group's partial (NCH is a multiple of the group size)
 #pragma unroll
                 for (int b = 0; b < 2; ++b) mbar_wait_spin(&bars->a2_free[t][b], (ubase + half - 1) & 1);
                 tc_fence_after();
                 {
-                    uint32_t part[16], cr[16];
+                    uint32_t part[16], px[16];
                     if constexpr (kTcGroup == 1) {   // one chunk per chain: the partial of chunk NCH - 2 is still unread too
-                        tmem_ld16(tbase + kColD2 + 16 * ((NCH - 2) & 1), part);
+                        const uint32_t d2 = tbase + kColD2 + 32 * ((NCH - 2) & 1);
+                        tmem_ld16(d2, part);
+                        tmem_ld16(d2 + 16, px);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int k = 0; k < K; ++k) acc[k] += __uint_as_float(part[k]);
+                        for (int k = 0; k < K; ++k) {
+                            acc[k] += __uint_as_float(part[k]);
+                            accx[k] += __uint_as_float(px[k]);
+                        }
                     }
-                    tmem_ld16(tbase + kColD2 + 16 * (((NCH - 1) / kTcGroup) & 1), part);
-                    tmem_ld16(tbase + kColD2X, cr);
+                    const uint32_t d2 = tbase + kColD2 + 32 * (((NCH - 1) / kTcGroup) & 1);
+                    tmem_ld16(d2, part);
+                    tmem_ld16(d2 + 16, px);
                     tmem_wait_ld();
+                    // undo the scalings (all exact powers of two): 2^-11 of the W_lo term, 2^-e of the point, 2^-q_k of the column
 #pragma unroll
-                    for (int k = 0; k < K; ++k) acc[k] = (acc[k] + __uint_as_float(part[k])) + __uint_as_float(cr[k]);
+                    for (int k = 0; k < K; ++k) {
+                        const float hk = acc[k] + __uint_as_float(part[k]);
+                        const float xk = accx[k] + __uint_as_float(px[k]);
+                        acc[k] = fmaf(xk, 1.0f / 2048.0f, hk) * inv_sc * cfg.tc_s2inv[f * kTcN2 + k];
+                    }
                 }
                 tc_fence_before();
                 // ---- hand the coefficients (+ b2 in fp32, Keras Dense) to the back-end warps ----
@@ -419,24 +471,22 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         // MMA issuer of tile t.  Ring cursors advance incrementally; descriptors differ only in their low word.
         // =====================================================================================================
         const int t = warp - kTcActWarps;
-        constexpr uint32_t id1 = tc_idesc(kTcChunk), id2 = tc_idesc(kTcN2), id2h = tc_idesc_f16(kTcN2);
+        constexpr uint32_t id1 = tc_idesc_f16(kTcChunk), id2 = tc_idesc_f16(2 * kTcN2), id2l = tc_idesc_f16(kTcN2);
         const uint32_t wbase = smem_u32(wring);
-        const uint64_t dB1 = tc_smem_desc(wbase, kTcChunk * 16, 128);
-        const uint64_t dB2 = tc_smem_desc(wbase + 2 * kTcB1Floats * 4, kTcN2 * 16, 128);
+        const uint64_t dB1 = tc_smem_desc(wbase, kTcChunk * 16, 128);                              // [k half][chunk rows][8 halfs]
+        const uint64_t dB2 = tc_smem_desc(wbase + kTcK1Max * kTcB1Halfs * 2, 2 * kTcN2 * 16, 128);   // [k half][32 rows][8 halfs]
         const uint32_t hi1 = (uint32_t)(dB1 >> 32), hi2 = (uint32_t)(dB2 >> 32);
         constexpr uint32_t kSlotStep = kTcChunkBytes >> 4;
+        const int nk1 = 3 * (cfg.d + 1) <= 16 ? 1 : 2;   // layer-1 k-steps in use
         uint32_t s1 = 0, p1 = 0;                    // ring slot / phase parity of the next chunk layer 1 consumes
-        uint32_t lo1 = (uint32_t)dB1;               // low descriptor word of that slot's B1hi tile
+        uint32_t lo1 = (uint32_t)dB1;               // low descriptor word of that slot's B1 tile
         uint32_t s2 = 0, lo2 = (uint32_t)dB2;       // ... layer 2 (its chunk was waited for by layer 1 two chunks earlier)
         const uint32_t tb = tmem + 256 * t;
         auto adv1 = [&]() { lo1 += kSlotStep; if (++s1 == kTcStages) { s1 = 0; p1 ^= 1; lo1 = (uint32_t)dB1; } };
         auto adv2 = [&]() { lo2 += kSlotStep; if (++s2 == kTcStages) { s2 = 0; lo2 = (uint32_t)dB2; } };
         auto l1 = [&](int b) {  // D1[b] = A1 . B1(slot s1)   (elected lane only)
-            mma_tf32_ts(tb + kColD1 + kTcChunk * b, tb + kColA1H, lo1, hi1, id1, 0u);
-#ifndef TCV_NO_L1X
-            mma_tf32_ts(tb + kColD1 + kTcChunk * b, tb + kColA1L, lo1, hi1, id1, 1u);
-            mma_tf32_ts(tb + kColD1 + kTcChunk * b, tb + kColA1H, lo1 + ((kTcB1Floats * 4) >> 4), hi1, id1, 1u);
-#endif
+            mma_f16_ts(tb + kColD1 + kTcChunk * b, tb + kColA1, lo1, hi1, id1, 0u);
+            if (nk1 > 1) mma_f16_ts(tb + kColD1 + kTcChunk * b, tb + kColA1 + 8, lo1 + ((kTcB1Halfs * 2) >> 4), hi1, id1, 1u);
             tc_commit(&bars->d1_full[t][b]);
         };
         uint32_t vseq = 0;
@@ -466,21 +516,16 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     tc_fence_after();
                     if (elect_one()) {
                         const int cc = c + b;
-                        const uint32_t d2 = tb + kColD2 + 16 * ((cc / kTcGroup) & 1), dx = tb + kColD2X;
-                        const uint32_t ah = tb + kColD1 + kTcChunk * b, al = tb + kColA2L + (kTcChunk / 2) * b;
-                        const uint32_t gfirst = (cc & (kTcGroup - 1)) == 0 ? 0u : 1u, ffirst = cc == 0 ? 0u : 1u;
+                        const uint32_t d2 = tb + kColD2 + 32 * ((cc / kTcGroup) & 1);
+                        const uint32_t a2 = tb + kColD1 + kTcChunk * b;
+                        const uint32_t gfirst = (cc & (kTcGroup - 1)) == 0 ? 0u : 1u;
 #pragma unroll
-                        for (int s = 0; s < kTcKSteps; ++s) {   // kind::tf32 k-step = 8 hidden units = a 512-byte B tile
-                            mma_tf32_ts(d2, ah + 8 * s, lo2 + s * 32, hi2, id2, s > 0 ? 1u : gfirst);                      // h_hi W_hi
+                        for (int s = 0; s < kTcKSteps; ++s) {   // k-step = 16 hidden units = 8 columns of fp16 pairs, a 1 KB B tile
+                            mma_f16_ts(d2, a2 + tc_a2_col(s), lo2 + s * ((kTcB2Halfs * 2) >> 4), hi2, id2, s > 0 ? 1u : gfirst);   // h_hi [W_hi | W_lo']
 #ifndef TCV_NO_L2X
-                            mma_tf32_ts(dx, ah + 8 * s, lo2 + s * 32 + ((kTcB2Floats * 4) >> 4), hi2, id2, s > 0 ? 1u : ffirst);  // h_hi W_lo
+                            mma_f16_ts(d2, a2 + tc_a2_col(s) + kTcBlk / 2, lo2 + s * ((kTcB2Halfs * 2) >> 4), hi2, id2l, 1u);      // h_lo W_hi
 #endif
                         }
-#ifndef TCV_NO_L2X
-#pragma unroll
-                        for (int s = 0; s < kTcKSteps16; ++s)   // kind::f16 k-step = 16 hidden units = 8 columns of fp16 pairs
-                            mma_f16_ts(dx, al + 8 * s, lo2 + s * 32 + ((2 * kTcB2Floats * 4) >> 4), hi2, id2h, 1u);          // h_lo W_hi
-#endif
                         tc_commit(&bars->a2_free[t][b]);
                         tc_commit(&bars->w_free[s2]);
                         if (more) l1(b);  // the activation warps read D1[b] before they signalled a2_full[b]
