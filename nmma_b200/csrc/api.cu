@@ -277,8 +277,7 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         for (float w : h->W2) w_ok = w_ok && std::isfinite(w);
         if (d + 1 <= 8 && K <= kTcN2 && w_ok) {
             int nch = (H + kTcChunk - 1) / kTcChunk;
-            nch = (nch + kTcGroup - 1) / kTcGroup * kTcGroup;  // whole layer-2 accumulation groups ...
-            nch = (nch + 1) / 2 * 2;                           // ... and an even count (two TMEM buffers per tile)
+            nch = (nch + kTcUnit - 1) / kTcUnit * kTcUnit;  // whole layer-2 accumulation groups (a multiple of the TMEM buffers per tile)
             c.tc_nch = nch;
             std::vector<float> tp((size_t)F * nch * kTcChunkFloats, 0.f), xs((size_t)F * 8, 0.f), s2inv((size_t)F * kTcN2, 1.f);
             auto pow2_scale = [](float vmax, int top) {   // 2^p with vmax 2^p in [2^(top-1), 2^top); 1 for an all-zero row

@@ -47,16 +47,29 @@
 
 namespace nmma {
 
-constexpr int kTcThreads = 640;
-constexpr int kTcActWarps = 8;
-constexpr int kTcBackWarp0 = 12;
+#ifndef TCV_SETS
+#define TCV_SETS 1
+#endif
+#ifndef TCV_BUFS
+#define TCV_BUFS 2
+#endif
+constexpr int kTcSets = TCV_SETS;            // activation-warp sets per tile: set s takes the chunks c = s (mod kTcSets)
+constexpr int kTcBufs = TCV_BUFS;            // layer-1 accumulator / layer-2 operand buffers per tile: chunk c uses buffer c % kTcBufs
+constexpr int kTcActWarps = 8 * kTcSets;     // sets x two tiles x four TMEM lane quadrants
+constexpr int kTcProdWarp = kTcActWarps + 2;
+constexpr int kTcOwnerWarp = kTcActWarps + 3;
+constexpr int kTcBackWarp0 = kTcActWarps + 4;
+constexpr int kTcThreads = 32 * (kTcBackWarp0 + 8);
 constexpr int kTcTile = 128;                 // points per tile = TMEM lanes
 constexpr int kTcTiles = 2;                  // tiles in flight per CTA
 #ifndef TCV_CHUNK
 #define TCV_CHUNK 64
 #endif
 constexpr int kTcChunk = TCV_CHUNK;          // hidden units per chunk = per act <-> issuer hand-off (N of the layer-1 MMA)
-constexpr int kTcBlk = (kTcChunk % 32 == 0) ? 32 : 16;   // columns per ReLU/split/store block: [h_hi pairs | h_lo pairs] in place
+#ifndef TCV_BLK
+#define TCV_BLK ((TCV_CHUNK % 32 == 0) ? 32 : 16)
+#endif
+constexpr int kTcBlk = TCV_BLK;   // columns per ReLU/split/store block: [h_hi pairs | h_lo pairs] in place
 constexpr int kTcKSteps = kTcChunk / 16;     // kind::f16 layer-2 k-steps (K = 16) per chunk
 constexpr int kTcN2 = 16;                    // layer-2 MMA N per term (n_coeff padded)
 constexpr int kTcK1Max = 2;                  // layer-1 k-steps staged (3 (d + 1) slots: d <= 4 uses one, d <= 7 two)
@@ -64,18 +77,26 @@ constexpr int kTcB1Halfs = kTcChunk * 16;    // one layer-1 B tile: [chunk hidde
 constexpr int kTcB2Halfs = 2 * kTcN2 * 16;   // one layer-2 B tile: [W_hi (16 coeff) | 2^11 W_lo (16 coeff)] x [16 hidden] fp16
 constexpr int kTcChunkFloats = (kTcK1Max * kTcB1Halfs + kTcKSteps * kTcB2Halfs) / 2;   // B1[0] | B1[1] | B2[k-steps] = 8 KB at 64
 constexpr uint32_t kTcChunkBytes = kTcChunkFloats * 4;
-constexpr int kTcStages = 6;                 // weight ring depth
+constexpr int kTcStages = (48 * 1024) / (int)kTcChunkBytes;   // weight ring depth (layer 1 runs kTcBufs chunks ahead of layer 2)
 // TMEM columns of one tile (tile t at column 256 t): everything layer 2 reads is written IN PLACE over the layer-1
 // accumulator block it came from (block of kTcBlk columns -> kTcBlk / 2 columns of h_hi fp16 pairs, then kTcBlk / 2 of h_lo).
-constexpr uint32_t kColD1 = 0;                       // 2 x chunk  layer-1 accumulators / layer-2 A operands
-constexpr uint32_t kColD2 = 2 * kTcChunk;            // 2 x 32     layer-2 partials [h W_hi | h_hi W_lo'], double buffered by group
-constexpr uint32_t kColA1 = 2 * kTcChunk + 64;       // 16         layer-1 A operand: fp16 pairs, 8 columns per k-step
+constexpr uint32_t kColD1 = 0;                       // bufs x chunk  layer-1 accumulators / layer-2 A operands
+constexpr uint32_t kColD2 = kTcBufs * kTcChunk;      // 2 x 32        layer-2 partials [h W_hi | h_hi W_lo'], double buffered by group
+constexpr uint32_t kColA1 = kTcBufs * kTcChunk + 64; // 16            layer-1 A operand: fp16 pairs, 8 columns per k-step
 static_assert(kColA1 + 16 <= 256, "TMEM columns per tile");
 static_assert(kTcChunk % 16 == 0 && kTcChunk >= 16 && kTcChunk <= 256, "layer-1 MMA N");
 #ifndef TCV_GROUP
-#define TCV_GROUP 2
+#define TCV_GROUP 4
 #endif
 constexpr int kTcGroup = TCV_GROUP;          // chunks per layer-2 accumulation chain (2 kTcKSteps MMAs each, RZ accumulate)
+// The partial of the group that chunk e closes is read while chunk e + kTcBufs is processed (its d1_full implies that layer 2
+// of chunk e is complete), by the set that owns that chunk: it must be the last set (it keeps the sums), and the read must come
+// before the group two further on restarts the accumulator at chunk e + kTcGroup + 1.
+static_assert(kTcBufs <= kTcGroup, "a group partial would be overwritten before it is read");
+static_assert(kTcSets == 1 || (kTcSets == 2 && kTcGroup % 2 == 0 && kTcBufs % 2 == 0), "groups must close on the last set's chunks");
+static_assert((kTcBufs & (kTcBufs - 1)) == 0 && (kTcGroup & (kTcGroup - 1)) == 0, "powers of two");
+constexpr int kTcUnit = kTcGroup;            // chunk counts (per filter, per hidden range) are multiples of this (>= kTcBufs)
+static_assert(kTcStages >= kTcBufs + 2, "weight ring too shallow");
 // TMEM column (relative to the chunk buffer) of the h_hi pairs of layer-2 k-step s; its h_lo pairs are kTcBlk / 2 further
 __host__ __device__ constexpr uint32_t tc_a2_col(int s) { return (uint32_t)(kTcBlk * (s / (kTcBlk / 16)) + 8 * (s % (kTcBlk / 16))); }
 
@@ -221,14 +242,22 @@ struct TcBars {
     uint64_t w_full[kTcStages], w_free[kTcStages];
     uint64_t b_full[2], b_free[2];
     uint64_t a1_full[kTcTiles];
-    uint64_t d1_full[kTcTiles][2];
-    uint64_t a2_full[kTcTiles][2], a2_free[kTcTiles][2];
+    uint64_t d1_full[kTcTiles][kTcBufs];
+    uint64_t a2_full[kTcTiles][kTcBufs], a2_free[kTcTiles][kTcBufs];
     uint64_t c_full[kTcTiles][2], c_free[kTcTiles][2];
     uint32_t tmem_base;
     uint32_t progress;   // bumped by the back-end warps once per (tile, filter): the watchdog's sign of life
     uint32_t finished;   // role warps that have left their loops
 };
 
+#ifdef TCV_TIMELINE   // debug build (tools/build_variants.py): clock64 stamps of one filter pass of CTA 0, printed at the end
+__device__ long long g_tc_tl[kTcTiles][64][10];
+#define TC_STAMP(t, c, k) do { if (blockIdx.x == 0 && vseq == 11 && (c) < 64 && lane == 0 && (warp & 3) == 0) g_tc_tl[t][c][k] = clock64(); } while (0)
+#define TC_STAMP_I(t, c, k) do { if (blockIdx.x == 0 && vseq == 11 && (c) < 64 && lane == 0) g_tc_tl[t][c][k] = clock64(); } while (0)
+#else
+#define TC_STAMP(t, c, k) do { } while (0)
+#define TC_STAMP_I(t, c, k) do { } while (0)
+#endif
 #ifdef TCV_SLEEP_PROD
 #define TC_WAIT_PROD(bar, par) mbar_wait_sleep(bar, par, TCV_SLEEP_PROD)
 #else
@@ -282,17 +311,19 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
 #define TC_PART_F0(w) (SPLIT ? (int)(((w) % nparts / hsplit) * F / fsplit) : 0)
 #define TC_PART_F1(w) (SPLIT ? (int)(((w) % nparts / hsplit + 1) * F / fsplit) : F)
 #define TC_PART_HS(w) ((SPLIT && COEFF) ? (int)((w) % nparts % hsplit) : 0)
-    const uint32_t half = (uint32_t)NCH >> 1;  // NCH is even: TMEM buffer = c & 1, its use count = vseq * half + (c >> 1)
+    const uint32_t uses = (uint32_t)NCH / kTcBufs;  // NCH is a multiple of kTcBufs: TMEM buffer = c % kTcBufs, its use count = vseq * uses + c / kTcBufs
 
     if (tid == 0) {
         for (int i = 0; i < kTcStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_free[i], kTcTiles); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_free[i], 8); }
         for (int t = 0; t < kTcTiles; ++t) {
             mbar_init(&bars->a1_full[t], 4);
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < kTcBufs; ++b) {
                 mbar_init(&bars->d1_full[t][b], 1);
                 mbar_init(&bars->a2_full[t][b], 4);
                 mbar_init(&bars->a2_free[t][b], 1);
+            }
+            for (int b = 0; b < 2; ++b) {
                 mbar_init(&bars->c_full[t][b], 4);
                 mbar_init(&bars->c_free[t][b], 4);
             }
@@ -301,7 +332,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         bars->finished = 0;
         mbar_fence_init();
     }
-    if (warp == 11) tmem_alloc(&bars->tmem_base, 512);
+    if (warp == kTcOwnerWarp) tmem_alloc(&bars->tmem_base, 512);
     if constexpr (!COEFF) {   // the coefficient mode has no back end: nothing to stage
         for (int i = tid; i < cfg.nobs * kObsRec; i += kTcThreads) s_obs[i] = cfg.o_pack[i];
         for (int i = tid; i < cfg.S; i += kTcThreads) s_samp[i] = cfg.samp[i];
@@ -313,9 +344,11 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
 
     if (warp < kTcActWarps) {
         // =====================================================================================================
-        // activation warps
+        // activation warps: set 0 owns the even chunks (TMEM buffer 0) and writes the layer-1 A operand, set 1 owns the odd
+        // chunks (buffer 1), sums the layer-2 partials (accumulation groups close on odd chunks) and hands the coefficients on
         // =====================================================================================================
-        const int t = warp >> 2;
+        const int set = kTcSets > 1 ? warp >> 3 : 0;
+        const int t = (warp >> 2) & 1;
         const int pidx = (warp & 3) * 32 + lane;
         const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(256 * t);
         uint32_t vseq = 0;  // (super-tile, filter) sequence number of this CTA
@@ -324,6 +357,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             const long long n = (item / nparts) * SUPER + (long long)t * kTcTile + pidx;
             const double* row = pts + (n < N ? n : 0) * cfg.P;
             for (int f = TC_PART_F0(item), f1 = TC_PART_F1(item); f < f1; ++f, ++vseq) {
+                const uint32_t ubase = vseq * uses;
                 // ---- layer-1 A operand (fp64 scaling, fp32 cast like Keras; then the exact power-of-two scalings of the
                 //      header comment and the fp16 hi/lo split): K slot 3 i + {0, 1, 2} = {hi_i, lo_i, hi_i} ----
                 bool okx = true;
@@ -347,70 +381,73 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     okx = okx && isfinite(S);
                     uint32_t eb = (__float_as_uint(S) >> 23) & 0xFFu;
                     eb = eb < 24u ? 24u : (eb > 230u ? 230u : eb);
-                    const float sc = okx ? __uint_as_float((257u - eb) << 23) : 0.f;
                     inv_sc = __uint_as_float((eb - 3u) << 23);
-                    __half hs[16 * kTcK1Max];
+                    if (set == 0) {
+                        const float sc = okx ? __uint_as_float((257u - eb) << 23) : 0.f;
+                        __half hs[16 * kTcK1Max];
 #pragma unroll
-                    for (int i = 0; i < 16 * kTcK1Max; ++i) hs[i] = __ushort_as_half((unsigned short)0);
+                        for (int i = 0; i < 16 * kTcK1Max; ++i) hs[i] = __ushort_as_half((unsigned short)0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        __half hi, lo;
-                        split_f16(okx ? xv[i] * sc : 0.f, hi, lo);
-                        hs[3 * i] = hi; hs[3 * i + 1] = lo; hs[3 * i + 2] = hi;
+                        for (int i = 0; i < 8; ++i) {
+                            __half hi, lo;
+                            split_f16(okx ? xv[i] * sc : 0.f, hi, lo);
+                            hs[3 * i] = hi; hs[3 * i + 1] = lo; hs[3 * i + 2] = hi;
+                        }
+                        uint32_t a1[8 * kTcK1Max];
+#pragma unroll
+                        for (int i = 0; i < 8 * kTcK1Max; ++i)
+                            a1[i] = (uint32_t)__half_as_ushort(hs[2 * i]) | ((uint32_t)__half_as_ushort(hs[2 * i + 1]) << 16);
+                        if (kTcSets > 1 && vseq > 0) {   // the previous filter's last layer-1 MMA (chunk NCH - 1) has read the old operand
+                            mbar_wait_spin(&bars->d1_full[t][kTcBufs - 1], (ubase - 1) & 1);
+                            tc_fence_after();
+                        }
+                        tmem_st16(tbase + kColA1, a1);
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->a1_full[t]);
                     }
-                    uint32_t a1[8 * kTcK1Max];
-#pragma unroll
-                    for (int i = 0; i < 8 * kTcK1Max; ++i)
-                        a1[i] = (uint32_t)__half_as_ushort(hs[2 * i]) | ((uint32_t)__half_as_ushort(hs[2 * i + 1]) << 16);
-                    tmem_st16(tbase + kColA1, a1);
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->a1_full[t]);
                 }
                 float acc[K], accx[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) { acc[k] = 0.f; accx[k] = 0.f; }
-                const uint32_t ubase = vseq * half;
-#pragma unroll 2
-                for (int c = 0; c < NCH; ++c) {
-                    const int b = c & 1;
-                    const uint32_t u = ubase + ((uint32_t)c >> 1);
-                    uint32_t v[kTcChunk];
+                for (int c = set; c < NCH; c += kTcSets) {
+                    const int b = c & (kTcBufs - 1);
+                    const uint32_t u = ubase + (uint32_t)c / kTcBufs;
+                    const uint32_t dbuf = tbase + kColD1 + kTcChunk * b;
+                    TC_STAMP(t, c, 0);
                     mbar_wait_spin(&bars->d1_full[t][b], u & 1);
                     tc_fence_after();
-#pragma unroll
-                    for (int blk = 0; blk < kTcChunk / kTcBlk; ++blk) {
-                        if constexpr (kTcBlk == 32) tmem_ld32(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, v + kTcBlk * blk);
-                        else tmem_ld16(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, v + kTcBlk * blk);
-                    }
-                    tmem_wait_ld();
+                    TC_STAMP(t, c, 1);
                     // ReLU + hi/lo split in kTcBlk-column blocks, [h_hi pairs | h_lo pairs] back in place: the store of one
-                    // block is in flight while the next block is computed
+                    // block is in flight while the next block is loaded and computed
 #pragma unroll
                     for (int blk = 0; blk < kTcChunk / kTcBlk; ++blk) {
-                        uint32_t o[kTcBlk];
+                        uint32_t v[kTcBlk], o[kTcBlk];
+                        if constexpr (kTcBlk == 32) tmem_ld32(dbuf + kTcBlk * blk, v);
+                        else tmem_ld16(dbuf + kTcBlk * blk, v);
+                        tmem_wait_ld();
 #ifndef TCV_NO_ALU   // TCV_*: compile-time timing experiments (tools/build_variants.py, profiles/r01_tc_experiments.md);
                      // a library built with any of them returns wrong numbers and only serves to time the skeleton
 #pragma unroll
                         for (int j = 0; j < kTcBlk / 2; ++j)
-                            relu_split_f16x2(__uint_as_float(v[kTcBlk * blk + 2 * j]), __uint_as_float(v[kTcBlk * blk + 2 * j + 1]),
-                                             o[j], o[kTcBlk / 2 + j]);
+                            relu_split_f16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), o[j], o[kTcBlk / 2 + j]);
 #else
 #pragma unroll
-                        for (int j = 0; j < kTcBlk; ++j) o[j] = v[kTcBlk * blk + j];
+                        for (int j = 0; j < kTcBlk; ++j) o[j] = v[j];
 #endif
-                        if constexpr (kTcBlk == 32) tmem_st32(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, o);
-                        else tmem_st16(tbase + kColD1 + kTcChunk * b + kTcBlk * blk, o);
+                        if constexpr (kTcBlk == 32) tmem_st32(dbuf + kTcBlk * blk, o);
+                        else tmem_st16(dbuf + kTcBlk * blk, o);
                     }
-                    if (c >= 2 && ((c - 2) & (kTcGroup - 1)) == kTcGroup - 1) {
-                        // layer 2 of chunk c - 2 is complete (layer 1 of this chunk was queued behind it and d1_full has
+                    TC_STAMP(t, c, 3);
+                    if (c >= kTcBufs && ((c - kTcBufs) & (kTcGroup - 1)) == kTcGroup - 1) {
+                        // layer 2 of chunk c - kTcBufs is complete (layer 1 of this chunk was queued behind it and d1_full has
                         // fired); it closed a group: add its partials.  The issuer reuses that accumulator only after
-                        // this warp's a2_full of a later chunk.
+                        // this warp's a2_full of a later chunk (it takes the chunks in order).
                         mbar_wait_spin(&bars->a2_free[t][b], (u - 1) & 1);
                         tc_fence_after();
                         uint32_t part[16], px[16];
-                        const uint32_t d2 = tbase + kColD2 + 32 * (((c - 2) / kTcGroup) & 1);
+                        const uint32_t d2 = tbase + kColD2 + 32 * (((c - kTcBufs) / kTcGroup) & 1);
                         tmem_ld16(d2, part);
                         tmem_ld16(d2 + 16, px);
                         tmem_wait_ld();
@@ -420,28 +457,21 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                             accx[k] += __uint_as_float(px[k]);
                         }
                     }
+                    TC_STAMP(t, c, 4);
                     tmem_wait_st();
                     tc_fence_before();  // orders the D1 / D2 loads and the operand stores before the issuer's next MMAs
                     __syncwarp();
+                    TC_STAMP(t, c, 5);
                     if (lane == 0) mbar_arrive(&bars->a2_full[t][b]);
+                    TC_STAMP(t, c, 6);
                 }
-                // drain: the last group's partial (NCH is a multiple of the group size)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) mbar_wait_spin(&bars->a2_free[t][b], (ubase + half - 1) & 1);
+                if (set != kTcSets - 1) continue;
+                // drain: the last group's partial (NCH is a multiple of the group size; the tensor pipe completes in order, so
+                // layer 2 of chunk NCH - 1 done means every MMA of the filter is done)
+                mbar_wait_spin(&bars->a2_free[t][kTcBufs - 1], (ubase + uses - 1) & 1);
                 tc_fence_after();
                 {
                     uint32_t part[16], px[16];
-                    if constexpr (kTcGroup == 1) {   // one chunk per chain: the partial of chunk NCH - 2 is still unread too
-                        const uint32_t d2 = tbase + kColD2 + 32 * ((NCH - 2) & 1);
-                        tmem_ld16(d2, part);
-                        tmem_ld16(d2 + 16, px);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            acc[k] += __uint_as_float(part[k]);
-                            accx[k] += __uint_as_float(px[k]);
-                        }
-                    }
                     const uint32_t d2 = tbase + kColD2 + 32 * (((NCH - 1) / kTcGroup) & 1);
                     tmem_ld16(d2, part);
                     tmem_ld16(d2 + 16, px);
@@ -499,21 +529,22 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         for (long long vv = 0; vv < total_v; ++vv, ++vseq) {
             mbar_wait_spin(&bars->a1_full[t], vseq & 1);
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {  // prologue: layer 1 of chunks 0 and 1
+            for (int b = 0; b < kTcBufs; ++b) {  // prologue: layer 1 of the first kTcBufs chunks
                 mbar_wait_spin(&bars->w_full[s1], p1);
                 tc_fence_after();
                 if (elect_one()) l1(b);
                 __syncwarp();
                 adv1();
             }
-            const uint32_t ubase = vseq * half;
-            for (int c = 0; c < NCH; c += 2) {
+            const uint32_t ubase = vseq * uses;
+            for (int c = 0; c < NCH; c += kTcBufs) {
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const bool more = c + b + 2 < NCH;
+                for (int b = 0; b < kTcBufs; ++b) {
+                    const bool more = c + b + kTcBufs < NCH;
                     if (more) mbar_wait_spin(&bars->w_full[s1], p1);
-                    mbar_wait_spin(&bars->a2_full[t][b], (ubase + ((uint32_t)c >> 1)) & 1);
+                    mbar_wait_spin(&bars->a2_full[t][b], (ubase + (uint32_t)c / kTcBufs) & 1);
                     tc_fence_after();
+                    TC_STAMP_I(t, c + b, 7);
                     if (elect_one()) {
                         const int cc = c + b;
                         const uint32_t d2 = tb + kColD2 + 32 * ((cc / kTcGroup) & 1);
@@ -531,12 +562,13 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                         if (more) l1(b);  // the activation warps read D1[b] before they signalled a2_full[b]
                     }
                     __syncwarp();
+                    TC_STAMP_I(t, c + b, 8);
                     adv2();
                     if (more) adv1();
                 }
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == kTcProdWarp) {
         // =====================================================================================================
         // TMA producer
         // =====================================================================================================
@@ -657,7 +689,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
             }
         }
     }
-    if (warp != 11) {
+    if (warp != kTcOwnerWarp) {
         __syncwarp();
         if (lane == 0) atomicAdd(&bars->finished, 1u);
     } else if (lane == 0) {
@@ -678,7 +710,18 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 11) tmem_dealloc(tmem, 512);
+#ifdef TCV_TIMELINE
+    if (blockIdx.x == 0 && tid == 0) {
+        const long long t0 = g_tc_tl[0][0][0];
+        for (int c = 0; c < NCH && c < 64; ++c)
+            for (int t = 0; t < kTcTiles; ++t) {
+                printf("tl tile %d chunk %2d:", t, c);
+                for (int k = 0; k < 9; ++k) printf(" %6lld", g_tc_tl[t][c][k] - t0);
+                printf("\n");
+            }
+    }
+#endif
+    if (warp == kTcOwnerWarp) tmem_dealloc(tmem, 512);
 #undef TC_PART_F0
 #undef TC_PART_F1
 #undef TC_PART_HS

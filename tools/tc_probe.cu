@@ -247,6 +247,94 @@ __global__ void __launch_bounds__(128) timing_kernel(int reps, int nwarps_issue,
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// kind::f16 (K = 16) timing and the per-chunk MMA pattern of fused_tc_logl_kernel (round 2, fp16 split operands):
+// per 64-hidden chunk 4 x (N = 32 MMA + N = 16 MMA into the same accumulator), commit, commit, one N = 64 MMA, commit.
+// Reports the cycles the elected lane needs to ISSUE the pattern and the cycles until the last commit has arrived.
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__host__ __device__ inline uint32_t make_idesc_f16(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24); }
+template <int MODE>   // 0: N=16 stream, 1: N=32 stream, 2: N=64 stream, 3: chunk pattern with commits, 4: chunk pattern, one commit
+__global__ void __launch_bounds__(128) f16_kernel(int reps, int nwarps_issue, long long* __restrict__ cycles) {
+    __shared__ __align__(128) float sB[MAXN * 8 * 4];
+    __shared__ __align__(8) uint64_t bar[8];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < MAXN * 8 * 4; i += 128) sB[i] = 0.0f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0u;
+    for (int c0 = 0; c0 < 64; c0 += 8) tmem_st8(tmem + lane_base + 384 + c0, a);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp < nwarps_issue) {
+        tc_fence_after();
+        const uint32_t dbase = tmem + warp * 128;
+        const uint32_t abase = tmem + 384;
+        const long long t0 = clock64();
+        long long t1 = t0;
+        if (elect_one()) {
+            if (MODE < 3) {
+                constexpr int N = MODE == 0 ? 16 : (MODE == 1 ? 32 : 64);
+                const uint64_t db = make_desc(smem_u32(sB), N * 16, 128);
+                for (int r = 0; r < reps; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) mma_f16_ts(dbase + (q & 1) * 64, abase + 8 * q, db, make_idesc_f16(N), r > 0 ? 1u : 0u);
+            } else {
+                const uint64_t db2 = make_desc(smem_u32(sB), 32 * 16, 128), db1 = make_desc(smem_u32(sB) + 4096, 64 * 16, 128);
+                for (int r = 0; r < reps; ++r) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        mma_f16_ts(dbase + 64, abase + 16 * (q >> 1) * 2 + 8 * (q & 1), db2 + q * 64, make_idesc_f16(32), q > 0 ? 1u : 0u);
+                        mma_f16_ts(dbase + 64, abase + 16 * (q >> 1) * 2 + 8 * (q & 1) + 16, db2 + q * 64, make_idesc_f16(16), 1u);
+                    }
+                    if (MODE == 3) { tc_commit(&bar[4 + warp]); tc_commit(&bar[6 + warp]); }
+                    mma_f16_ts(dbase, abase + 56, db1, make_idesc_f16(64), 0u);
+                    if (MODE == 3) tc_commit(&bar[2 + warp]);
+                }
+            }
+            t1 = clock64();
+            tc_commit(&bar[warp]);
+        }
+        __syncwarp();
+        mbar_wait(&bar[warp], 0);
+        if ((tid & 31) == 0) { cycles[2 * warp] = clock64() - t0; }
+        if (t1 != t0) cycles[2 * warp + 1] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+template <int MODE>
+void run_f16(const char* name, int per_rep, long long* dC) {
+    for (int nw : {1, 2}) {
+        const int reps = 1024;
+        f16_kernel<MODE><<<1, 128>>>(reps, nw, dC);
+        CK(cudaDeviceSynchronize());
+        long long c[4];
+        CK(cudaMemcpy(c, dC, 32, cudaMemcpyDeviceToHost));
+        printf("[f16] %s, issuing warps=%d: %.1f cycles per %s until complete, %.1f to issue (per warp)\n", name, nw,
+               (double)c[0] / reps / (per_rep ? 1 : 4), per_rep ? "chunk pattern" : "MMA", (double)c[1] / reps / (per_rep ? 1 : 4));
+    }
+}
+
 template <int N, int NACC, int TS>
 void run_timing(long long* dC) {
     for (int nw : {1, 2}) {
@@ -356,6 +444,11 @@ int main() {
                (double)c / (2 * reps));
     }
 
+    run_f16<0>("kind::f16 N=16 K=16 A=TMEM", 0, dC);
+    run_f16<1>("kind::f16 N=32 K=16 A=TMEM", 0, dC);
+    run_f16<2>("kind::f16 N=64 K=16 A=TMEM", 0, dC);
+    run_f16<3>("chunk pattern (8 L2 MMAs, 2 commits, 1 L1 MMA, commit)", 1, dC);
+    run_f16<4>("chunk pattern without the commits", 1, dC);
     run_timing<16, 1, 1>(dC);
     run_timing<16, 2, 1>(dC);
     run_timing<16, 4, 1>(dC);
