@@ -408,9 +408,9 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                         if (lane == 0) mbar_arrive(&bars->a1_full[t]);
                     }
                 }
-                float acc[K], accx[K];
+                float acc[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) { acc[k] = 0.f; accx[k] = 0.f; }
+                for (int k = 0; k < K; ++k) acc[k] = 0.f;
                 for (int c = set; c < NCH; c += kTcSets) {
                     const int b = c & (kTcBufs - 1);
                     const uint32_t u = ubase + (uint32_t)c / kTcBufs;
@@ -419,25 +419,39 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     mbar_wait_spin(&bars->d1_full[t][b], u & 1);
                     tc_fence_after();
                     TC_STAMP(t, c, 1);
-                    // ReLU + hi/lo split in kTcBlk-column blocks, [h_hi pairs | h_lo pairs] back in place: the store of one
-                    // block is in flight while the next block is loaded and computed
+                    // ReLU + hi/lo split in kTcBlk-column blocks, [h_hi pairs | h_lo pairs] back in place.  The load of block
+                    // blk + 1 is issued before block blk is computed (ptxas tracks each tcgen05.ld's registers on its own
+                    // scoreboard: the wait below costs nothing for a load that is not consumed yet), the store of block blk is
+                    // in flight while block blk + 1 is computed.
+                    constexpr int NB = kTcChunk / kTcBlk;
+                    uint32_t v[2][kTcBlk];
+                    auto load_blk = [&](int blk, uint32_t* dst) {
+                        if constexpr (kTcBlk == 32) tmem_ld32(dbuf + kTcBlk * blk, dst);
+                        else tmem_ld16(dbuf + kTcBlk * blk, dst);
+                    };
+                    load_blk(0, v[0]);
 #pragma unroll
-                    for (int blk = 0; blk < kTcChunk / kTcBlk; ++blk) {
-                        uint32_t v[kTcBlk], o[kTcBlk];
-                        if constexpr (kTcBlk == 32) tmem_ld32(dbuf + kTcBlk * blk, v);
-                        else tmem_ld16(dbuf + kTcBlk * blk, v);
+                    for (int blk = 0; blk < NB; ++blk) {
+                        uint32_t o[kTcBlk];
+                        const uint32_t* vc = v[blk & 1];
+#ifdef TCV_PREFETCH
+                        if (blk + 1 < NB) load_blk(blk + 1, v[(blk + 1) & 1]);
+#endif
                         tmem_wait_ld();
 #ifndef TCV_NO_ALU   // TCV_*: compile-time timing experiments (tools/build_variants.py, profiles/r01_tc_experiments.md);
                      // a library built with any of them returns wrong numbers and only serves to time the skeleton
 #pragma unroll
                         for (int j = 0; j < kTcBlk / 2; ++j)
-                            relu_split_f16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), o[j], o[kTcBlk / 2 + j]);
+                            relu_split_f16x2(__uint_as_float(vc[2 * j]), __uint_as_float(vc[2 * j + 1]), o[j], o[kTcBlk / 2 + j]);
 #else
 #pragma unroll
-                        for (int j = 0; j < kTcBlk; ++j) o[j] = v[j];
+                        for (int j = 0; j < kTcBlk; ++j) o[j] = vc[j];
 #endif
                         if constexpr (kTcBlk == 32) tmem_st32(dbuf + kTcBlk * blk, o);
                         else tmem_st16(dbuf + kTcBlk * blk, o);
+#ifndef TCV_PREFETCH
+                        if (blk + 1 < NB) load_blk(blk + 1, v[(blk + 1) & 1]);
+#endif
                     }
                     TC_STAMP(t, c, 3);
                     if (c >= kTcBufs && ((c - kTcBufs) & (kTcGroup - 1)) == kTcGroup - 1) {
@@ -451,11 +465,9 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                         tmem_ld16(d2, part);
                         tmem_ld16(d2 + 16, px);
                         tmem_wait_ld();
+                        // one running sum per coefficient: the W_lo term (staged times 2^11) joins its group's partial first
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            acc[k] += __uint_as_float(part[k]);
-                            accx[k] += __uint_as_float(px[k]);
-                        }
+                        for (int k = 0; k < K; ++k) acc[k] += fmaf(__uint_as_float(px[k]), 1.0f / 2048.0f, __uint_as_float(part[k]));
                     }
                     TC_STAMP(t, c, 4);
                     tmem_wait_st();
@@ -478,11 +490,9 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     tmem_wait_ld();
                     // undo the scalings (all exact powers of two): 2^-11 of the W_lo term, 2^-e of the point, 2^-q_k of the column
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const float hk = acc[k] + __uint_as_float(part[k]);
-                        const float xk = accx[k] + __uint_as_float(px[k]);
-                        acc[k] = fmaf(xk, 1.0f / 2048.0f, hk) * inv_sc * cfg.tc_s2inv[f * kTcN2 + k];
-                    }
+                    for (int k = 0; k < K; ++k)
+                        acc[k] = (acc[k] + fmaf(__uint_as_float(px[k]), 1.0f / 2048.0f, __uint_as_float(part[k]))) * inv_sc *
+                                 cfg.tc_s2inv[f * kTcN2 + k];
                 }
                 tc_fence_before();
                 // ---- hand the coefficients (+ b2 in fp32, Keras Dense) to the back-end warps ----

@@ -39,7 +39,7 @@ def _paths(lik, pts, cols):
             eng.set_option("no_fast_backend", 0)
         eng.set_option("points_per_thread", 0)
     if eng.get_info("tc_supported"):
-        eng.set_option("path", 3)                             # tcgen05 3xTF32 kernel
+        eng.set_option("path", 3)                             # tcgen05 kernel (fp16 hi/lo split operands)
         out["fused_tc"] = eng.logl_host(pts)                  # small batches: filters split over CTAs (launch_tc.cu)
         eng.set_option("no_filter_split", 1)
         out["fused_tc_unsplit"] = eng.logl_host(pts)          # the throughput instantiation on the same points
@@ -106,7 +106,7 @@ def test_bu2019lm_device_tensor_and_large_batch(torch_cuda):
     small.set_option("path", 2)
     two = small.logl_host(base)
     small.set_option("path", 0)
-    # the automatic path at this N is the tcgen05 kernel (3xTF32 split, round-toward-zero accumulator): measured
+    # the automatic path at this N is the tcgen05 kernel (fp16 hi/lo split operands, round-toward-zero accumulator): measured
     # 1.8e-6 relative against the fp32 two-stage kernels, 50x inside the 1e-4 north-star tolerance
     assert_logl_close(unperm[0], two, rtol=1e-5)
     assert small.get_info("tc_supported") == 1
@@ -190,7 +190,7 @@ def test_mlp_fp32_accuracy_vs_fp64_truth(torch_cuda):
     pts = np.concatenate([x, np.full((256, 1), 40.0), np.zeros((256, 3))], axis=1)   # [x, dL, timeshift, redshift, Ebv]
     eng.set_option("path", 2)                      # plain two-stage kernels: fp32 FFMA front end (coeff_mlp_kernel)
     got = eng.coeffs(pts).cpu().numpy()
-    eng.set_option("path", 0)                      # >= 128 points: the tensor-core kernel in coefficient mode (3xTF32 split)
+    eng.set_option("path", 0)                      # >= 128 points: the tensor-core kernel in coefficient mode (fp16 hi/lo split)
     got_tc = eng.coeffs(pts).cpu().numpy()
     for fi, f in enumerate(filters):
         W1, b1, W2, b2 = core[f]["model"]
@@ -200,11 +200,11 @@ def test_mlp_fp32_accuracy_vs_fp64_truth(torch_cuda):
         e_gpu = np.abs(got[:, fi, :] - exact).max()
         e_np = np.abs(npf32 - exact).max()
         e_tc = np.abs(got_tc[:, fi, :] - exact).max()
-        print(f, "gpu fp32 err", e_gpu, "numpy fp32 err", e_np, "tensor-core 3xTF32 err", e_tc)
+        print(f, "gpu fp32 err", e_gpu, "numpy fp32 err", e_np, "tensor-core fp16 hi/lo split err", e_tc)
         assert e_gpu < 2e-5 and e_gpu < 4 * e_np + 1e-6
-        # 3xTF32 drops the lo x lo products and the tensor core accumulates with round-toward-zero (group partials are
-        # added with RN on the CUDA cores): ~1e-5 absolute on these trained weights (coefficients of order 1-10), i.e.
-        # < 1e-4 mag through (maxs - mins) VA -- a factor 10 inside the 1e-3 mag budget, a factor 6 above fp32 FFMA
+        # the split drops the lo x lo products and the tensor core accumulates with round-toward-zero (group partials are
+        # added with RN on the CUDA cores): <= ~1e-5 absolute on these trained weights (coefficients of order 1-10), i.e.
+        # < 1e-4 mag through (maxs - mins) VA -- a factor 10 inside the 1e-3 mag budget
         assert e_tc < 3e-5
 
 
