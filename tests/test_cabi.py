@@ -83,7 +83,7 @@ def test_sass_tensor_core_kernel_is_tcgen05():
     counts = {op: len(re.findall(r"\b" + op, body))
               for op in ("UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "SYNCS", "FHFMA", r"F2FP\.RELU")}
     # 9 MMAs per 64-hidden chunk (+ the prologue), in-place [h_hi | h_lo] stores of 32 columns
-    assert counts["UTCHMMA"] >= 18 and counts["LDTM"] >= 4 and counts["STTM"] >= 4, counts
+    assert counts["UTCHMMA"] >= 18 and counts["LDTM"] >= 4 and counts["STTM"] >= 3, counts
     # the 2-instruction-per-hidden-unit ReLU + fp16 hi/lo split: F2FP.RELU (cvt.{rz,rn}.relu.f16x2.f32) + FHFMA (fma.f32.f16)
     assert counts["FHFMA"] >= 64 and counts[r"F2FP\.RELU"] >= 64, counts
     assert counts["UTCBAR"] >= 4 and counts["UBLKCP"] >= 2 and counts["SYNCS"] >= 20, counts

@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "nmma_b200", "lib", "libnmma_b200.so")
 KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "UTCCP", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "FFMA2", "FFMA", "DFMA",
-       "HMMA", "LDS", "LDG", "STG", "FADD", "LOP3", "F2FP", "MUFU", "ELECT")
+       "HMMA", "LDS", "LDG", "STG", "FADD", "LOP3", "F2FP", "FHFMA", "MUFU", "ELECT")
 
 
 def kernel_sass(substr):
