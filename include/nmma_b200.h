@@ -266,8 +266,9 @@ int nmma_b200_get_info(nmma_b200_t* h, const char* key, int64_t* value);
  * (SURVEY.md 8d): runs `iters` dependent-chain FMA rounds on every SM and returns
  * the achieved FLOP/s for scalar (variant 0) or packed f32x2 (variant 1) FMAs. */
 int nmma_b200_ffma_peak(nmma_b200_t* h, int variant, int iters, double* flops_per_s);
-/* Dense tcgen05 kind::tf32 rate (the tensor-core kernel's roofline denominator): `iters` x 2
- * MMAs of 128x128x8 per SM, A from TMEM, B from shared memory; FLOP/s over all SMs. */
+/* Dense tcgen05 kind::tf32 rate: `iters` x 2 MMAs of 128x128x8 per SM, A from TMEM, B from shared
+ * memory; FLOP/s over all SMs.  (Roofline denominator of the round-1 tf32-split kernel; the current
+ * kernel runs kind::f16 MMAs and is reported against the dense bf16/fp16 rate, twice this one.) */
 int nmma_b200_tf32_peak(nmma_b200_t* h, int iters, double* flops_per_s);
 /* fp64 FMA rate (the GP front end's roofline denominator), same construction as ffma_peak. */
 int nmma_b200_dfma_peak(nmma_b200_t* h, int iters, double* flops_per_s);
