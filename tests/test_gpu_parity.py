@@ -495,3 +495,52 @@ def test_abi_error_paths(torch_cuda):
     assert ei.value.code == L.ERR_STATE
     with pytest.raises(L.NmmaB200Error):
         KilonovaEngine(10 ** 6)
+
+
+def test_tensor_core_fp16_staging_dynamic_range(torch_cuda):
+    """The tensor-core front end carries every fp32 operand as two fp16 values; what keeps them in the fp16 range are exact
+    power-of-two scalings (rows of [W1; b1], columns of W2, one scale per point and filter -- csrc/tc_kernel.cuh).  Weights whose
+    rows / columns differ by many orders of magnitude and points far outside the training range must come out as close to
+    the exact (fp64) network as the fp32 FFMA kernel does."""
+    torch = torch_cuda
+    from nmma_b200.em import SVDLightCurveModel
+    filters = ["ztfr", "sdssu", "2massks"]
+    core = fixture_core("mlp", filters)
+    rng = np.random.default_rng(11)
+    row_scale = np.array([1e-5, 3e2, 1.0])             # layer-1 rows: 7.5 orders of magnitude apart
+    col_scale = 10.0 ** rng.uniform(-6, 4, size=10)    # layer-2 columns: 10 orders
+    for f in filters:
+        W1, b1, W2, b2 = (np.array(a, dtype=np.float32) for a in core[f]["model"])
+        W1 = (W1 * row_scale[:, None]).astype(np.float32)
+        b1 = (b1 * np.float32(1e-3)).astype(np.float32)
+        W2 = (W2 * col_scale[None, :]).astype(np.float32)
+        W2[::7] *= np.float32(1e-9)                     # entries far below their column's maximum (fp16 subnormal remainders)
+        b2 = (b2 * col_scale).astype(np.float32)
+        core[f]["model"] = (W1, b1, W2, b2)
+    model = SVDLightCurveModel("Bu2019nsbh", svd_mag_model=core, interpolation_type="tensorflow", filters=filters)
+    eng = model._canonical_engine(np.asarray(model.model_times, float))
+    lo, hi = core[filters[0]]["param_mins"], core[filters[0]]["param_maxs"]
+    # scaled inputs from 1e-4 to 1e4 times the training range, both signs, and the exact corners 0 and 1
+    mag = 10.0 ** rng.uniform(-4, 4, size=(512, 3)) * rng.choice([-1.0, 1.0], size=(512, 3))
+    mag[:8] = rng.integers(0, 2, size=(8, 3))
+    x = lo + mag * (hi - lo)
+    pts = np.concatenate([x, np.full((512, 1), 40.0), np.zeros((512, 3))], axis=1)   # [x, dL, timeshift, redshift, Ebv]
+    eng.set_option("path", 2)                      # plain two-stage kernels: fp32 FFMA front end (coeff_mlp_kernel)
+    got = eng.coeffs(pts).cpu().numpy()
+    eng.set_option("path", 0)                      # >= 128 points: the tensor-core kernel in coefficient mode
+    got_tc = eng.coeffs(pts).cpu().numpy()
+    assert np.isfinite(got_tc).all()
+    for fi, f in enumerate(filters):
+        W1, b1, W2, b2 = core[f]["model"]
+        xs = ((x - core[f]["param_mins"]) / (core[f]["param_maxs"] - core[f]["param_mins"])).astype(np.float32)
+        h = np.maximum(xs.astype(np.float64) @ W1.astype(np.float64) + b1, 0)
+        exact = h @ W2.astype(np.float64) + b2
+        # what the rounding errors are relative to: sum_i |x_i W1_ij| + |b1_j| per hidden unit (layer 1 may cancel), through |W2|
+        h_abs = np.abs(xs.astype(np.float64)) @ np.abs(W1.astype(np.float64)) + np.abs(b1)
+        scale = h_abs @ np.abs(W2.astype(np.float64)) + np.abs(b2)
+        e_ffma = (np.abs(got[:, fi, :] - exact) / scale).max()
+        e_tc = (np.abs(got_tc[:, fi, :] - exact) / scale).max()
+        print(f, "relative to sum |x W1| |W2|: FFMA", e_ffma, "tensor core", e_tc)
+        # measured: FFMA 3.5-4.3e-8, tensor core 1.9-2.4e-7 (22-bit operands, round-toward-zero accumulation in chains of 32 MMAs)
+        assert e_ffma < 2e-7
+        assert e_tc < 1e-6
