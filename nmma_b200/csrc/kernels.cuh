@@ -420,7 +420,20 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+#ifdef TCV_HINT   // timing experiment: try_wait with a suspend-time hint (ns): the hardware parks the warp until the phase completes
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)TCV_HINT)
+            : "memory");
+    } while (!ok);
+#else
     while (!mbar_try_wait(bar, parity)) {}
+#endif
 }
 // Wait of a warp that is far ahead of its producer (back-end and TMA-producer warps of the tensor-core kernel): it leaves
 // the scheduler between polls, so its polling does not take issue slots from the activation warps of its sub-partition.
