@@ -38,3 +38,8 @@ def one(spec):
 with ThreadPoolExecutor(8) as ex:
     for name, spills in ex.map(one, sys.argv[1:]):
         print(name, spills[:4])
+if g.DEV:   # the dev shortcut relinked nmma_b200/lib/libnmma_b200.so without most instantiations: put the full library back
+    env = {k: v for k, v in os.environ.items() if k != "NMMA_DEV_BUILD"}
+    subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT, env=env, check=True,
+                   stdout=subprocess.DEVNULL)
+    print("[build_variants] full library restored")
