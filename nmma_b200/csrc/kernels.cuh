@@ -431,6 +431,17 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)TCV_HINT)
             : "memory");
     } while (!ok);
+#elif defined(TCV_TESTWAIT)   // timing experiment: non-blocking test_wait in a tight loop (lowest wake-up latency, most issue slots)
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
 #else
     while (!mbar_try_wait(bar, parity)) {}
 #endif

@@ -77,7 +77,10 @@ constexpr int kTcB1Halfs = kTcChunk * 16;    // one layer-1 B tile: [chunk hidde
 constexpr int kTcB2Halfs = 2 * kTcN2 * 16;   // one layer-2 B tile: [W_hi (16 coeff) | 2^11 W_lo (16 coeff)] x [16 hidden] fp16
 constexpr int kTcChunkFloats = (kTcK1Max * kTcB1Halfs + kTcKSteps * kTcB2Halfs) / 2;   // B1[0] | B1[1] | B2[k-steps] = 8 KB at 64
 constexpr uint32_t kTcChunkBytes = kTcChunkFloats * 4;
-constexpr int kTcStages = (48 * 1024) / (int)kTcChunkBytes;   // weight ring depth (layer 1 runs kTcBufs chunks ahead of layer 2)
+#ifndef TCV_RING_KB
+#define TCV_RING_KB 48
+#endif
+constexpr int kTcStages = (TCV_RING_KB * 1024) / (int)kTcChunkBytes;   // weight ring depth (layer 1 runs kTcBufs chunks ahead of layer 2)
 // TMEM columns of one tile (tile t at column 256 t): everything layer 2 reads is written IN PLACE over the layer-1
 // accumulator block it came from (block of kTcBlk columns -> kTcBlk / 2 columns of h_hi fp16 pairs, then kTcBlk / 2 of h_lo).
 constexpr uint32_t kColD1 = 0;                       // bufs x chunk  layer-1 accumulators / layer-2 A operands
