@@ -177,7 +177,7 @@ int nmma_b200_logl(nmma_b200_t* h, const double* points_dev /* N*P */, int64_t N
                    double* out_dev /* N */, void* stream);
 /* Same through HOST buffers: pinned staging, H2D, kernels, D2H, synchronised on return.
  * This is the call an unmodified one-point-at-a-time sampler ends up in.  Large batches
- * are cut into row blocks (option "pipeline_blocks", default 6) whose copies overlap the
+ * are cut into row blocks (one wave first, then option "pipeline_blocks", default 6) whose copies overlap the
  * kernels of their neighbours on separate streams.  Both pointers must be host memory. */
 int nmma_b200_logl_host(nmma_b200_t* h, const double* points_host, int64_t N, double* out_host);
 /* Same input side, but the result stays on the GPU in out_dev[N] (no D2H copy): the sharded
