@@ -30,7 +30,7 @@ int ensure_tc_smem(nmma_b200_t* h, size_t smem) {
 }
 
 template <bool FAST>
-int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st) {
+int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cudaStream_t st, bool per_filter = false) {
     constexpr int K = 10;
     const size_t smem = tc_smem_bytes(K, h->T, h->cfg.S, h->cfg.nobs);
     if (int rc = ensure_tc_smem<K, FAST, true, false>(h, smem)) return rc;
@@ -41,8 +41,18 @@ int launch_tc_f(nmma_b200_t* h, const double* pts, long long N, double* out, cud
     if (h->opt_max_ctas > 0) grid = std::min<long long>(grid, h->opt_max_ctas);
     // small batches: a 256-point super-tile takes ~205 us on one SM whatever N is, so when the super-tiles leave SMs idle
     // the filters of each are spread over several CTAs (per-part sums, combined in a fixed order)
+    // large batches whose last wave would leave more than half of the SMs idle: whole waves with the un-split kernel, the
+    // rest with ONE FILTER PER WORK ITEM spread over all SMs (e.g. 10^6 points = 26 waves + 59 super-tiles -> 26.5 instead of
+    // 27 rounds).  One part per filter, added in filter order, is the association of the un-split kernel's running sum:
+    // a row's log-likelihood does not depend on which side of the cut it is (test_bu2019lm_device_tensor_and_large_batch).
+    if (!h->opt_no_fsplit && !per_filter && nsuper > grid && (nsuper % grid) > 0 && (nsuper % grid) * 2 <= grid) {
+        const long long n_main = (nsuper / grid) * grid * super;
+        if (int rc = launch_tc_f<FAST>(h, pts, n_main, out, st)) return rc;
+        return launch_tc_f<FAST>(h, pts + n_main * h->cfg.P, N - n_main, out + n_main, st, true);
+    }
     int fsplit = 1;
-    if (!h->opt_no_fsplit && nsuper * 2 <= grid) fsplit = (int)std::min<long long>(h->F, grid / nsuper);
+    if (per_filter) fsplit = h->F;
+    else if (!h->opt_no_fsplit && nsuper * 2 <= grid) fsplit = (int)std::min<long long>(h->F, grid / nsuper);
     double* dst = out;
     if (fsplit > 1) {
         const size_t need = (size_t)N * fsplit;
