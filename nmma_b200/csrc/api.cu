@@ -275,6 +275,22 @@ int finalize(nmma_b200_t* h, bool need_obs) {
         for (float w : h->W1) w_ok = w_ok && std::isfinite(w);
         for (float w : h->b1) w_ok = w_ok && std::isfinite(w);
         for (float w : h->W2) w_ok = w_ok && std::isfinite(w);
+        // ... and the per-point scale is an exponent-field computation clamped to 2^-100 .. 2^100: rows / columns whose
+        // largest entry is outside 2^-60 .. 2^60 keep the tensor-core path off as well (the FFMA kernel takes over)
+        auto sane = [](float vmax) { return !(vmax > 0.f) || (vmax > 8.7e-19f && vmax < 1.1e18f); };
+        for (int f = 0; f < F && w_ok; ++f) {
+            for (int i = 0; i <= d && w_ok; ++i) {
+                float vmax = 0.f;
+                for (int j = 0; j < H; ++j)
+                    vmax = std::max(vmax, std::fabs(i < d ? h->W1[((size_t)f * d + i) * H + j] : h->b1[(size_t)f * H + j]));
+                w_ok = sane(vmax);
+            }
+            for (int o = 0; o < K && w_ok; ++o) {
+                float vmax = 0.f;
+                for (int j = 0; j < H; ++j) vmax = std::max(vmax, std::fabs(h->W2[((size_t)f * H + j) * K + o]));
+                w_ok = sane(vmax);
+            }
+        }
         if (d + 1 <= 8 && K <= kTcN2 && w_ok) {
             int nch = (H + kTcChunk - 1) / kTcChunk;
             nch = (nch + kTcUnit - 1) / kTcUnit * kTcUnit;  // whole layer-2 accumulation groups (a multiple of the TMEM buffers per tile)

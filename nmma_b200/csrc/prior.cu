@@ -260,8 +260,10 @@ int nmma_b200_logl_sweep(nmma_b200_t* h, uint64_t seed, int64_t first_index, int
     if (!out_dev) return fail(h, NMMA_B200_ERR_ARG, "logl_sweep: NULL device pointer");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // block = 2^20 points: 8 P MB of drawn points (48 MB at P = 6) stay in the 126 MB L2 between the two kernels
-    const long long block = std::min<long long>(N, 1ll << 20);
+    // block ~ 2^20 points: 8 P MB of drawn points (48 MB at P = 6) stay in the 126 MB L2 between the two kernels; whole
+    // waves of the persistent throughput kernels (256 points per SM), so that no block ends in a partly filled round
+    const long long wave = (long long)h->sm_count * 256;
+    const long long block = std::min<long long>(N, std::max<long long>(wave, (1ll << 20) / wave * wave));
     if (!points_dev && (size_t)block * h->P > h->sweep_cap) {
         if (h->sweep_scratch) cudaFree(h->sweep_scratch);
         h->sweep_scratch = nullptr; h->sweep_cap = 0;
