@@ -111,9 +111,9 @@ int launch_tc_coeff_parts(nmma_b200_t* h, const double* pts, long long N, float*
     const long long nsuper = (N + super - 1) / super;
     const long long grid_max = h->opt_max_ctas > 0 ? std::min<long long>(h->sm_count, h->opt_max_ctas) : h->sm_count;
     const int fsplit = (int)std::max<long long>(1, std::min<long long>(h->F, grid_max / nsuper));
-    // hidden ranges: a power of two that leaves every range whole accumulation groups (tc_kernel.cuh: kTcUnit chunks)
+    // hidden ranges: a power of two that leaves every range whole accumulation groups (in parts mode: kTcBufs chunks)
     int hsplit = 1;
-    while (nsuper * fsplit * (hsplit * 2) <= grid_max && h->cfg.tc_nch % (hsplit * 2 * kTcUnit) == 0) hsplit *= 2;
+    while (nsuper * fsplit * (hsplit * 2) <= grid_max && h->cfg.tc_nch % (hsplit * 2 * kTcBufs) == 0) hsplit *= 2;
     const long long grid = std::max<long long>(1, std::min(grid_max, nsuper * fsplit * hsplit));
     fused_tc_logl_kernel<K, false, true, true><<<(unsigned)grid, kTcThreads, smem, st>>>(
         h->cfg, pts, N, reinterpret_cast<double*>(parts), fsplit, hsplit);

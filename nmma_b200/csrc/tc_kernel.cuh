@@ -97,7 +97,7 @@ constexpr int kTcGroup = TCV_GROUP;          // chunks per layer-2 accumulation 
 // before the group two further on restarts the accumulator at chunk e + kTcGroup + 1.
 static_assert(kTcBufs <= kTcGroup, "a group partial would be overwritten before it is read");
 static_assert(kTcSets == 1 || (kTcSets == 2 && kTcGroup % 2 == 0 && kTcBufs % 2 == 0), "groups must close on the last set's chunks");
-static_assert((kTcBufs & (kTcBufs - 1)) == 0 && (kTcGroup & (kTcGroup - 1)) == 0, "powers of two");
+static_assert((kTcBufs & (kTcBufs - 1)) == 0 && (kTcGroup & (kTcGroup - 1)) == 0 && kTcGroup <= 8, "powers of two");
 constexpr int kTcUnit = kTcGroup;            // chunk counts (per filter, per hidden range) are multiples of this (>= kTcBufs)
 static_assert(kTcStages >= kTcBufs + 2, "weight ring too shallow");
 // TMEM column (relative to the chunk buffer) of the h_hi pairs of layer-2 k-step s; its h_lo pairs are kTcBlk / 2 further
@@ -286,6 +286,10 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
     // [N][F][hsplit][cfg.K] (no b2), and backend_logl_parts_kernel adds them in range order before it scores them
     const bool parts_mode = SPLIT && COEFF && hsplit_arg > 0;   // hsplit_arg = 0: plain coefficient mode (fp64, + b2)
     const int hsplit = parts_mode ? hsplit_arg : 1;
+    // chunks per layer-2 accumulation chain: kTcGroup; in parts mode the minimum (kTcBufs), so that the hidden layer can be cut
+    // into twice as many ranges (one-point latency).  Folds to the constant in the throughput instantiations.
+    const int gsz = (COEFF && SPLIT && parts_mode) ? kTcBufs : kTcGroup;
+    const int gsh = gsz == 1 ? 0 : (gsz == 2 ? 1 : (gsz == 4 ? 2 : 3));
     const int nparts = fsplit * hsplit;
     // Work item = (256-point super-tile, filter part): with fsplit > 1 (small batches, launch_tc.cu) the filters of one
     // super-tile are spread over fsplit CTAs and `out` receives the per-part sums [N][fsplit] (NaN = failed) that
@@ -457,14 +461,14 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
 #endif
                     }
                     TC_STAMP(t, c, 3);
-                    if (c >= kTcBufs && ((c - kTcBufs) & (kTcGroup - 1)) == kTcGroup - 1) {
+                    if (c >= kTcBufs && ((c - kTcBufs) & (gsz - 1)) == gsz - 1) {
                         // layer 2 of chunk c - kTcBufs is complete (layer 1 of this chunk was queued behind it and d1_full has
                         // fired); it closed a group: add its partials.  The issuer reuses that accumulator only after
                         // this warp's a2_full of a later chunk (it takes the chunks in order).
                         mbar_wait_spin(&bars->a2_free[t][b], (u - 1) & 1);
                         tc_fence_after();
                         uint32_t part[16], px[16];
-                        const uint32_t d2 = tbase + kColD2 + 32 * (((c - kTcBufs) / kTcGroup) & 1);
+                        const uint32_t d2 = tbase + kColD2 + 32 * (((c - kTcBufs) >> gsh) & 1);
                         tmem_ld16(d2, part);
                         tmem_ld16(d2 + 16, px);
                         tmem_wait_ld();
@@ -487,7 +491,7 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                 tc_fence_after();
                 {
                     uint32_t part[16], px[16];
-                    const uint32_t d2 = tbase + kColD2 + 32 * (((NCH - 1) / kTcGroup) & 1);
+                    const uint32_t d2 = tbase + kColD2 + 32 * (((NCH - 1) >> gsh) & 1);
                     tmem_ld16(d2, part);
                     tmem_ld16(d2 + 16, px);
                     tmem_wait_ld();
@@ -560,9 +564,9 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     TC_STAMP_I(t, c + b, 7);
                     if (elect_one()) {
                         const int cc = c + b;
-                        const uint32_t d2 = tb + kColD2 + 32 * ((cc / kTcGroup) & 1);
+                        const uint32_t d2 = tb + kColD2 + 32 * ((cc >> gsh) & 1);
                         const uint32_t a2 = tb + kColD1 + kTcChunk * b;
-                        const uint32_t gfirst = (cc & (kTcGroup - 1)) == 0 ? 0u : 1u;
+                        const uint32_t gfirst = (cc & (gsz - 1)) == 0 ? 0u : 1u;
 #pragma unroll
                         for (int s = 0; s < kTcKSteps; ++s) {   // k-step = 16 hidden units = 8 columns of fp16 pairs, a 1 KB B tile
                             mma_f16_ts(d2, a2 + tc_a2_col(s), lo2 + s * ((kTcB2Halfs * 2) >> 4), hi2, id2, s > 0 ? 1u : gfirst);   // h_hi [W_hi | W_lo']
