@@ -576,8 +576,43 @@ __device__ __forceinline__ float fast_log_ndtr(float b) {
 }
 
 // Per-(point, filter) scalars of the FAST back end and the systematics-node cache of one thread.
+// Shared-space loads by 32-bit shared address (SA instantiations of the FAST back end): a generic pointer into dynamic shared
+// memory makes ptxas re-derive the shared window base (S2UR SR_CgaCtaId, ULEA, the carve-up arithmetic) at every use under
+// register pressure -- ~60 of ~120 instructions per observation in the tensor-core kernel's back end.  The base addresses are
+// made opaque once (sa_opaque: the result of a volatile asm cannot be rematerialised) and the loads are plain ld.shared.
+__device__ __forceinline__ uint32_t sa_opaque(const void* smem_ptr) {
+    uint32_t a = smem_u32(smem_ptr), o;
+    asm volatile("mov.u32 %0, %1;" : "=r"(o) : "r"(a));
+    return o;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int2 lds_i2(uint32_t a) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
 struct FastFilt {
     const float2* bq;   // float2 row-pair basis pack of the filter (shared or global memory)
+    uint32_t bq_sa, obs_sa, samp_sa;   // SA instantiations: the same tables by shared address
     int T, lo, hi;
     float ga, gb, dmz, dlt, dhi;
     double z1, tsh;
@@ -600,32 +635,34 @@ __device__ __forceinline__ bool fast_filt_setup(const DevCfg& cfg, int f, const 
     return true;
 }
 // One observation (record k of observed filter g, mapped directly onto the filter of `ff`) of the FAST back end.
-template <int K>
+template <int K, bool SA = false>
 __device__ __forceinline__ double fast_obs_term(const DevCfg& cfg, const FastFilt& ff, const float (&c)[K], int g, int k,
                                                 const double* __restrict__ row, const double* __restrict__ s_obs,
                                                 const double* __restrict__ s_samp, SysCache& syc) {
     double out = 0.0;
     const double* rec = s_obs + k * kObsRec;
-    const float4 rf = *reinterpret_cast<const float4*>(rec + 6);  // (float)t, (float)mag, 1/sigma, log(sigma)+C
-    const int2 cls = *reinterpret_cast<const int2*>(rec + 8);      // class, left systematics node
-    const double t = rec[0];
+    const uint32_t rsa = SA ? ff.obs_sa + (uint32_t)k * (kObsRec * 8) : 0u;
+    auto samp_at = [&](int j) { return SA ? lds_f64(ff.samp_sa + (uint32_t)j * 8u) : s_samp[j]; };
+    const float4 rf = SA ? lds_f4(rsa + 48) : *reinterpret_cast<const float4*>(rec + 6);  // (float)t, (float)mag, 1/sigma, log(sigma)+C
+    const int2 cls = SA ? lds_i2(rsa + 64) : *reinterpret_cast<const int2*>(rec + 8);      // class, left systematics node
+    const double t = SA ? lds_f64(rsa) : rec[0];
     const float gq = fmaf(rf.x, ff.ga, ff.gb);
     int j = __float2int_rd(gq);
     const float fr = gq - (float)j;
     bool inr = true;
     double tj;
     if (j >= ff.lo && j < ff.hi && fr > ff.dlt && fr < ff.dhi) {
-        tj = __dadd_rn(__dmul_rn(s_samp[j], ff.z1), ff.tsh);
+        tj = __dadd_rn(__dmul_rn(samp_at(j), ff.z1), ff.tsh);
     } else {  // cold: range ends and near-node cases, settled with the exact comparisons
-        const double tlo = __dadd_rn(__dmul_rn(s_samp[ff.lo], ff.z1), ff.tsh);
-        const double thi = __dadd_rn(__dmul_rn(s_samp[ff.hi], ff.z1), ff.tsh);
+        const double tlo = __dadd_rn(__dmul_rn(samp_at(ff.lo), ff.z1), ff.tsh);
+        const double thi = __dadd_rn(__dmul_rn(samp_at(ff.hi), ff.z1), ff.tsh);
         if (!(t >= tlo && t <= thi)) {
             inr = false;  // np.interp left = right = +inf
             tj = 0.0; j = ff.lo;
         } else {
             j = locate(cfg, ff.lo, ff.hi, t, ff.z1, ff.tsh);
             if (j >= ff.hi) j = ff.hi - 1;  // t == t_hi: weight 1 on the last interval
-            tj = __dadd_rn(__dmul_rn(s_samp[j], ff.z1), ff.tsh);
+            tj = __dadd_rn(__dmul_rn(samp_at(j), ff.z1), ff.tsh);
         }
     }
     float mu = CUDART_INF_F;
@@ -633,12 +670,16 @@ __device__ __forceinline__ double fast_obs_term(const DevCfg& cfg, const FastFil
         const float wgt = (float)__dsub_rn(t, tj) * ff.ga;
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
+        uint32_t ba = SA ? ff.bq_sa + (uint32_t)j * 8u : 0u;
+        const uint32_t bstep = (uint32_t)ff.T * 8u;
+#pragma unroll
         for (int i = 0; i < K; ++i) {
-            const float2 v = ff.bq[i * ff.T + j];
+            const float2 v = SA ? lds_f2(ba) : ff.bq[i * ff.T + j];
+            ba += bstep;
             d0 = fmaf(v.x, c[i], d0);
             d1 = fmaf(v.y, c[i], d1);
         }
-        const float2 sc = ff.bq[K * ff.T + j], mn = ff.bq[(K + 1) * ff.T + j];
+        const float2 sc = SA ? lds_f2(ba) : ff.bq[K * ff.T + j], mn = SA ? lds_f2(ba + bstep) : ff.bq[(K + 1) * ff.T + j];
         const float a0 = fmaf(d0, sc.x, mn.x), a1 = fmaf(d1, sc.y, mn.y);
         mu = fmaf(wgt, a1 - a0, a0) + ff.dmz;
     }
@@ -651,11 +692,11 @@ __device__ __forceinline__ double fast_obs_term(const DevCfg& cfg, const FastFil
     } else if (cls.x == kObsSampled || cls.x == kObsUpper) {
         // sigma_sys at this observation time: the bracketing nodes and the weight are fixed per observation
         // (systematics.py:288-291 through np.interp with 'constant' ends); the node values are per point
-        const int2 nd = *reinterpret_cast<const int2*>(rec + 9);     // right node, weight bits
-        const float2 sl = *reinterpret_cast<const float2*>(rec + 10);  // sigma_obs^2, detection limit
+        const int2 nd = SA ? lds_i2(rsa + 72) : *reinterpret_cast<const int2*>(rec + 9);     // right node, weight bits
+        const float2 sl = SA ? lds_f2(rsa + 80) : *reinterpret_cast<const float2*>(rec + 10);  // sigma_obs^2, detection limit
         float ssys;
         if (cls.y < 0) {
-            ssys = *reinterpret_cast<const float*>(rec + 11);          // constant budget
+            ssys = SA ? lds_f32(rsa + 88) : *reinterpret_cast<const float*>(rec + 11);          // constant budget
         } else {
             if (cls.y != syc.cur0 || nd.x != syc.cur1) {   // warp-uniform: all lanes walk the same observation list
                 syc.cur0 = cls.y; syc.cur1 = nd.x;
@@ -696,14 +737,17 @@ __device__ __forceinline__ double fast_obs_term(const DevCfg& cfg, const FastFil
     return out;
 }
 
-template <int K, bool FAST, typename CT>
+// SA = true: bp / s_obs / s_samp are in shared memory and sa[3] = their opaque shared addresses (sa_opaque), FAST only.
+template <int K, bool FAST, typename CT, bool SA = false>
 __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, const CT (&cp)[K], const PointScal& ps,
                                                     const double* __restrict__ row, const double* __restrict__ bp,
-                                                    const double* __restrict__ s_obs, const double* __restrict__ s_samp) {
+                                                    const double* __restrict__ s_obs, const double* __restrict__ s_samp,
+                                                    const uint32_t* sa = nullptr) {
     double lsum = 0.0;
     if constexpr (FAST) {
         FastFilt ff;
         if (!fast_filt_setup(cfg, f, ps, bp, ff)) return CUDART_NAN;
+        if constexpr (SA) { ff.bq_sa = sa[0]; ff.obs_sa = sa[1]; ff.samp_sa = sa[2]; }
         float c[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) c[i] = (float)cp[i];
@@ -711,7 +755,7 @@ __device__ __forceinline__ double fused_filter_logl(const DevCfg& cfg, int f, co
             const int g = cfg.f_glist[gi];
             const int k1 = cfg.g_off[g + 1];
             SysCache syc;   // warp-uniform: all lanes walk the same observation list
-            for (int k = cfg.g_off[g]; k < k1; ++k) lsum += fast_obs_term<K>(cfg, ff, c, g, k, row, s_obs, s_samp, syc);
+            for (int k = cfg.g_off[g]; k < k1; ++k) lsum += fast_obs_term<K, SA>(cfg, ff, c, g, k, row, s_obs, s_samp, syc);
         }
     } else {
         const double ext = ext_mag(cfg, f, ps);

@@ -634,6 +634,9 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
         // =====================================================================================================
         const int t = (warp - kTcBackWarp0) >> 2;
         const int pidx = ((warp - kTcBackWarp0) & 3) * 32 + lane;
+        // shared addresses of the back end's tables, opaque to the optimiser (kernels.cuh: sa_opaque)
+        const uint32_t basis_sa0 = sa_opaque(s_basis0), basis_sa1 = sa_opaque(s_basis0 + bslot);
+        const uint32_t obs_sa = sa_opaque(s_obs), samp_sa = sa_opaque(s_samp);
         uint32_t vseq = 0;
         for (long long it = 0; it < my_super; ++it) {
             const long long item = blockIdx.x + it * gridDim.x;
@@ -685,7 +688,12 @@ fused_tc_logl_kernel(const DevCfg cfg, const double* __restrict__ pts, long long
                     } else
 #endif
                     if constexpr (FAST) {
+#ifndef TCV_NO_SA
+                        const uint32_t sa[3] = {slot ? basis_sa1 : basis_sa0, obs_sa, samp_sa};
+                        logl += fused_filter_logl<K, true, float, true>(cfg, f, cf, ps, row, basis, s_obs, s_samp, sa);
+#else
                         logl += fused_filter_logl<K, true>(cfg, f, cf, ps, row, basis, s_obs, s_samp);
+#endif
                     } else {
                         double cp[K];
 #pragma unroll
