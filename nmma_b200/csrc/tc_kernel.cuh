@@ -19,11 +19,13 @@
 // The tensor core adds into its fp32 accumulator with round-toward-zero (profiles/r01_tc_probe.txt), so layer 2
 // accumulates in chains of kTcGroup chunks whose partials the CUDA cores sum with round-to-nearest adds.
 //
-// What bounds it (profiles/r01_tc_experiments.md): not the tensor pipe, not TMEM bandwidth and not the back end, but the
-// per-chunk hand-offs (mbarrier wake-up, tcgen05.ld / st + wait, MMA issue by one thread, tcgen05.commit) and the
-// activation warps' instruction stream.  Hence: h_hi / h_lo go back IN PLACE over the layer-1 accumulator they came
-// from (one tcgen05.st per 32 hidden units), [W_hi | 2^11 W_lo] is ONE N = 32 B tile (h_hi needs one MMA per 16 hidden
-// units for both terms), and K = 16 per MMA: 9 MMAs per 64-hidden chunk instead of 23 with tf32 operands.
+// What bounds it (profiles/r01_tc_experiments.md, r02_tc_f16_experiments.md): not the tensor pipe (25 % active), not TMEM
+// bandwidth, not the weight stream, but the activation warps' dispatch-port time (3.0 issue cycles per hidden unit and point
+// for the split -- F2FP holds the port for 2 -- plus their tcgen05.ld / st) and the per-chunk hand-offs.  Hence: h_hi / h_lo go
+// back IN PLACE over the layer-1 accumulator they came from (one tcgen05.st per 32 hidden units), [W_hi | 2^11 W_lo] is ONE
+// N = 32 B tile (h_hi needs one MMA per 16 hidden units for both terms), and K = 16 per MMA: 9 MMAs per 64-hidden chunk
+// instead of 23 with tf32 operands.  More activation-warp sets, more TMEM buffers, other chunk widths (TCV_SETS, TCV_BUFS,
+// TCV_CHUNK, TCV_GROUP: compile-time experiments, only the defaults are parity-tested on every path) measured no faster.
 //
 // Work decomposition (one persistent CTA per SM, 20 warps, two 128-point tiles in flight):
 //   warps 0-3 / 4-7    activation warps of tile 0 / 1: thread = one parameter point = one TMEM lane.  Per filter they
