@@ -110,6 +110,10 @@ def test_bu2019lm_device_tensor_and_large_batch(torch_cuda):
     # 1.8e-6 relative against the fp32 two-stage kernels, 50x inside the 1e-4 north-star tolerance
     assert_logl_close(unperm[0], two, rtol=1e-5)
     assert small.get_info("tc_supported") == 1
+    # the same rows through HOST buffers: the copy / compute pipeline (one-wave first block, whole-wave blocks, a last partial
+    # block) must return what the one-launch device path returns, bit for bit, whatever block a row lands in
+    host = lik.log_likelihood_batch(np.ascontiguousarray(pts[perm]), cols)
+    assert isinstance(host, np.ndarray) and np.array_equal(host, out), "host pipeline and device path disagree"
 
 
 # ------------------------------------------------------------------------------------------------
