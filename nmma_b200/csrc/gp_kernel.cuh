@@ -31,6 +31,9 @@
 // compile-time offsets, and the polynomial coefficients in __constant__ memory: 20.9, 19.3 and 20.0 M evals/s -- every
 // constant that lands in a vector register turns a 2-operand DFMA into a 3-operand one; 128-bit loads of the alphas:
 // 20.8 M, the kernel sits at the 128-register limit and ten more live registers spill).
+// Also tried: a warp-uniform fast path without the exponent clamp (host-computed r^2 bound per filter, __all_sync per training
+// row, two instances of the row body): 9.05 -> 10.46 ms per 2e5 evaluations -- the vote, the branch and the doubled loop body
+// cost more than the one integer min per value they save.
 // gf_pow is restated operation by operation in tests/test_rq_pow.py (accuracy vs a 40-digit reference).
 #pragma once
 #include "kernels.cuh"
