@@ -431,9 +431,22 @@ def gpu_arm(args):
     if world > 1:      # after the CPU arm has forked its workers: staging buffers and copy threads on the GPU's own NUMA node
         from nmma_b200.sharding import bind_to_gpu_numa_node
         numa = bind_to_gpu_numa_node(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        # NCCL prints its version banner on stdout when the first communicator comes up (NCCL_DEBUG=VERSION in some
+        # environments): stdout carries ONE JSON line, so file descriptor 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     sh = ShardedEvaluator(lambda p: None) if world > 1 else None
 
     def sync():
