@@ -293,3 +293,28 @@ def test_combined_model_container_stacks_fluxes():
     assert np.array_equal(rt, tj)
     for f in lcj:
         assert np.array_equal(lcj[f], rlcj[f]), f
+
+
+def test_fp16_split_operand_scheme_emulated():
+    """CPU emulation (tools/tc_numerics.py: mlp_f16x3) of the tensor-core front end's operand scheme -- fp16 hi/lo pairs, exact
+    power-of-two scalings of the rows of [W1; b1], of the columns of W2 and of every point, h_hi rounded toward zero with the
+    ReLU -- on the trained Bu2019nsbh fixture weights: as close to the fp64 network as NumPy's fp32, and the scaled
+    activations stay below 2^14 (the bound csrc/tc_kernel.cuh relies on) for inputs far outside the training range."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import tc_numerics as T
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bu2019nsbh_fixture.npz"), allow_pickle=True)
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-0.1, 1.5, size=(512, 3)), 10.0 ** rng.uniform(-4, 4, size=(256, 3)) * rng.choice([-1, 1], (256, 3))])
+    for f in ("ztfr", "sdssu", "2massks"):
+        W1, b1, W2, b2 = (z[f"{f}/{n}"] for n in ("W1", "b1", "W2", "b2"))
+        xa = np.concatenate([x.astype(np.float32), np.ones((len(x), 1), np.float32)], 1)
+        Wa = np.concatenate([W1, b1[None, :]], 0).astype(np.float32)
+        h = np.maximum(xa.astype(np.float64) @ Wa.astype(np.float64), 0)
+        exact = h @ W2.astype(np.float64) + b2
+        scale = (np.abs(xa.astype(np.float64)) @ np.abs(Wa.astype(np.float64))) @ np.abs(W2.astype(np.float64)) + np.abs(b2)
+        got = T.mlp_f16x3(x, W1, b1, W2, b2)                       # asserts 2^e relu(v) < 2^14 inside
+        fp32 = T.mm32(np.maximum(T.mm32(xa, Wa), 0), W2) + b2
+        e_split = (np.abs(got - exact) / scale).max()
+        e_fp32 = (np.abs(fp32 - exact) / scale).max()
+        assert e_split < 2e-7 and e_split < 4 * e_fp32 + 2e-8, (f, e_split, e_fp32)
